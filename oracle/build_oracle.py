@@ -1,0 +1,28 @@
+#!/usr/bin/env python3
+"""Compile the C restatement oracle/rm_oracle.c -> oracle/librm_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Strict IEEE fp32, no FMA contraction (the pinned semantics, see the header of rm_oracle.c).
+The .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "rm_oracle.c")
+OUT = os.path.join(HERE, "librm_oracle.so")
+
+
+def build(verbose: bool = True, force: bool = False) -> str:
+    if (not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= os.path.getmtime(SRC)):
+        return OUT
+    cmd = ["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
+           "-Wall", "-Wextra", SRC, "-o", OUT, "-lm"]
+    if verbose:
+        print("[build_oracle]", " ".join(cmd))
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)
