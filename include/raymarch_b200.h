@@ -1,0 +1,130 @@
+/* raymarch_b200.h -- C ABI of libraymarch_b200.so
+ *
+ * Drop-in boundary for the one hot path of thi-ng/raymarchcl: the OpenCL pipeline
+ *   {:write [p-buf v-buf]} -> per pass {:write [o-buf mc-buf]} + kernel "RenderImage"
+ *   -> {:write q-buf} + kernel "TonemapImage" + blocking read of q-buf
+ * that /root/reference/src/thi/ng/raymarchcl/core.clj:76-97 (make-pipeline) describes and
+ * core.clj:171 / :204 (ops/execute-pipeline) runs through thi.ng/simplecl -> JOCL.
+ * A JVM host keeps render-options + structgen unchanged and swaps execute-pipeline for these
+ * calls via JNA. Plain pointers and sizes only; no C++/torch types.
+ *
+ * Data conventions (identical to what the reference uploads):
+ *   voxels  uint8[rz][ry][rx], index z*rx*ry + y*rx + x           (renderer.cl:167, io.clj:19-33)
+ *   opts    the 544-byte TRenderOpts blob produced by sg/encode    (renderer.cl:35-78, core.clj:105)
+ *   mc      16384 float4 = 65536 floats, the scatter table         (renderer.cl:143, core.clj:138)
+ *   accum   float4[W*H] RGBA accumulator ("p-buf")                 (core.clj:144)
+ *   argb    uint32[W*H] 0xFFRRGGBB ("q-buf", what :read [:out] returns) (renderer.cl:503-506)
+ *
+ * Errors: every call returns RM_OK (0) or a negative rm_status; nothing throws or aborts across
+ * the ABI; rm_last_error() returns the message of the last failure on that context (or of the
+ * last failed rm_create when ctx == NULL).
+ * Threading: a context may be used from one thread at a time; distinct contexts are independent.
+ * Ownership: the caller owns every host pointer; the library has copied what it needs when a
+ * call returns. All device memory belongs to the context.
+ */
+#ifndef RAYMARCH_B200_H
+#define RAYMARCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RM_OPTS_BYTES   544    /* sizeof(TRenderOpts), renderer.cl:35-78 */
+#define RM_TABLE_FLOATS 65536  /* 0x4000 float4, renderer.cl:143 / core.clj:138 */
+#define RM_ABI_VERSION  1
+
+typedef struct rm_ctx rm_ctx;
+
+typedef enum rm_status {
+  RM_OK = 0,
+  RM_ERR_INVALID_ARG = -1,   /* null pointer, wrong blob size, non-positive extent ... */
+  RM_ERR_BAD_OPTS = -2,      /* TRenderOpts disagrees with the uploaded volume / framebuffer */
+  RM_ERR_NO_VOLUME = -3,     /* render before rm_set_volume */
+  RM_ERR_NO_FRAMEBUFFER = -4,/* render / tonemap / read before rm_clear_accum */
+  RM_ERR_CUDA = -5,          /* a CUDA runtime call failed; see rm_last_error */
+  RM_ERR_NO_DEVICE = -6,     /* no usable sm_100 device */
+  RM_ERR_UNSUPPORTED = -7
+} rm_status;
+
+/* Work and timing of the calls since the last rm_reset_stats (or rm_create).
+ * steps / taps / outer_iters are REFERENCE-EQUIVALENT counts: iterations of the inner march loop
+ * (renderer.cl:219-234), calls of voxelLookupI (renderer.cl:172-178) and iterations of the
+ * sphere-trace loop (renderer.cl:243-251) that the reference would execute on the same inputs.
+ * They are gathered only while counting is enabled (rm_set_option RM_OPT_COUNT_WORK). */
+typedef struct rm_stats {
+  uint64_t steps;
+  uint64_t taps;
+  uint64_t outer_iters;
+  uint64_t pixel_samples;   /* pixels x passes rendered */
+  uint64_t kernel_launches; /* CUDA kernels launched by this context */
+  double   render_ms;       /* device time of RenderImage-equivalent kernels (CUDA events) */
+  double   tonemap_ms;      /* device time of TonemapImage-equivalent kernels */
+  double   h2d_ms, d2h_ms;  /* device time of copies issued by this context */
+  uint64_t h2d_bytes, d2h_bytes;
+} rm_stats;
+
+typedef enum rm_option {
+  RM_OPT_COUNT_WORK = 1,   /* 0 (default) | 1: gather reference-equivalent work counters */
+  RM_OPT_KERNEL = 2        /* 0 = default fast kernel; 1 = plain one-thread-per-pixel kernel */
+} rm_option;
+
+/* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */
+int  rm_abi_version(void);
+int  rm_device_count(void);
+int  rm_create(int device_id, rm_ctx** out_ctx);
+void rm_destroy(rm_ctx* ctx);
+const char* rm_last_error(const rm_ctx* ctx);
+
+/* ---- inputs ---- */
+/* v-buf upload (vio/load-volume, io.clj:19-33 + {:write [.. v-buf]}, core.clj:81). */
+int rm_set_volume(rm_ctx* ctx, const uint8_t* voxels, int rx, int ry, int rz);
+/* p-buf / q-buf allocation + zero fill (ops/init-buffers core.clj:140-145, {:write [p-buf ..]} :81). */
+int rm_clear_accum(rm_ctx* ctx, int width, int height);
+
+/* ---- the hot path ---- */
+/* One {:write [o-buf mc-buf]} + "RenderImage" launch (core.clj:84-89): host opts + table in,
+ * accumulator updated in place on the device. */
+int rm_render_pass(rm_ctx* ctx, const void* opts, size_t opts_len, const float* mc, size_t mc_floats);
+/* All `iter` passes of a frame in submission order, from host buffers (core.clj:82-90).
+ * opts[i] / mc[i] are per-pass pointers, as make-render-option-buffer / :mc-buffers hold them. */
+int rm_render_frame(rm_ctx* ctx, const void* const* opts, const float* const* mc, int iter);
+/* "TonemapImage" with pass-0 opts + :read [:out] (core.clj:91-97): ARGB words to host memory. */
+int rm_tonemap(rm_ctx* ctx, const void* opts, size_t opts_len, uint32_t* argb_out);
+/* Parity hook: copy the fp32 RGBA accumulator to the host (the reference never reads p-buf). */
+int rm_read_accum(rm_ctx* ctx, float* rgba_out);
+
+/* ---- resident-input variants (inputs already in HBM when the timed region starts) ---- */
+/* Store the per-pass opts blobs and tables on the device once (test-anim keeps them across frames,
+ * core.clj:189-208) ... */
+int rm_upload_passes(rm_ctx* ctx, const void* const* opts, const float* const* mc, int iter);
+/* ... then render passes [first, first+count) from the resident copies; no host traffic. */
+int rm_render_resident(rm_ctx* ctx, int first, int count);
+/* Tonemap into device memory the caller owns (e.g. a torch tensor used for the NCCL gather);
+ * `packed` != 0 writes only this context's tile shard, tile-major (see rm_set_tile_shard). */
+int rm_tonemap_device(rm_ctx* ctx, const void* opts, size_t opts_len, void* d_argb, int packed);
+/* Copy the accumulator into device memory the caller owns (same packing rule). */
+int rm_copy_accum_device(rm_ctx* ctx, void* d_rgba, int packed);
+int rm_sync(rm_ctx* ctx);
+/* Issue all further work of this context on a CUDA stream the caller owns (a cudaStream_t passed
+ * as void*; NULL restores the context's own stream), so that the caller's events time it. */
+int rm_set_stream(rm_ctx* ctx, void* cuda_stream);
+
+/* ---- multi-GPU: interleaved tile ownership ---- */
+/* This context renders only tiles t with t % world == rank, tiles being tile_w x tile_h pixel
+ * rectangles numbered row-major. world == 1 (default) renders everything. */
+int rm_set_tile_shard(rm_ctx* ctx, int rank, int world, int tile_w, int tile_h);
+/* Number of pixels this context owns under the current shard and framebuffer. */
+int64_t rm_shard_pixels(const rm_ctx* ctx);
+
+/* ---- options, stats ---- */
+int rm_set_option(rm_ctx* ctx, int option, int64_t value);
+int rm_get_stats(const rm_ctx* ctx, rm_stats* out);
+int rm_reset_stats(rm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYMARCH_B200_H */

@@ -1,0 +1,91 @@
+"""ctypes binding of libraymarch_b200.so (include/raymarch_b200.h).
+
+This is the same C ABI a JVM host binds through JNA. There is NO CPU fallback:
+if the shared library is missing or no sm_100 device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libraymarch_b200.so")
+
+OPTS_BYTES = 544
+TABLE_FLOATS = 65536
+
+RM_OK = 0
+STATUS_NAMES = {0: "RM_OK", -1: "RM_ERR_INVALID_ARG", -2: "RM_ERR_BAD_OPTS", -3: "RM_ERR_NO_VOLUME",
+                -4: "RM_ERR_NO_FRAMEBUFFER", -5: "RM_ERR_CUDA", -6: "RM_ERR_NO_DEVICE", -7: "RM_ERR_UNSUPPORTED"}
+RM_OPT_COUNT_WORK = 1
+RM_OPT_KERNEL = 2
+
+# every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_set_volume",
+    "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
+    "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
+    "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_set_option", "rm_get_stats",
+    "rm_reset_stats",
+]
+
+
+class RmStats(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("taps", C.c_uint64), ("outer_iters", C.c_uint64),
+                ("pixel_samples", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("render_ms", C.c_double), ("tonemap_ms", C.c_double),
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class RaymarchError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libraymarch_b200.so (built in-tree by raymarchcl_b200/csrc/build.py). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python raymarchcl_b200/csrc/build.py` "
+            "(or __graft_entry__.build()). There is no CPU fallback for the render op.")
+    lib = C.CDLL(LIB_PATH)
+    vp, ip, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.rm_abi_version.restype = ip
+    lib.rm_device_count.restype = ip
+    lib.rm_create.argtypes = [ip, C.POINTER(vp)]
+    lib.rm_destroy.argtypes = [vp]
+    lib.rm_destroy.restype = None
+    lib.rm_last_error.argtypes = [vp]
+    lib.rm_last_error.restype = C.c_char_p
+    lib.rm_set_volume.argtypes = [vp, vp, ip, ip, ip]
+    lib.rm_clear_accum.argtypes = [vp, ip, ip]
+    lib.rm_render_pass.argtypes = [vp, vp, sz, vp, sz]
+    lib.rm_render_frame.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
+    lib.rm_tonemap.argtypes = [vp, vp, sz, vp]
+    lib.rm_read_accum.argtypes = [vp, vp]
+    lib.rm_upload_passes.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
+    lib.rm_render_resident.argtypes = [vp, ip, ip]
+    lib.rm_tonemap_device.argtypes = [vp, vp, sz, vp, ip]
+    lib.rm_copy_accum_device.argtypes = [vp, vp, ip]
+    lib.rm_sync.argtypes = [vp]
+    lib.rm_set_stream.argtypes = [vp, vp]
+    lib.rm_set_tile_shard.argtypes = [vp, ip, ip, ip, ip]
+    lib.rm_shard_pixels.argtypes = [vp]
+    lib.rm_shard_pixels.restype = C.c_int64
+    lib.rm_set_option.argtypes = [vp, ip, C.c_int64]
+    lib.rm_get_stats.argtypes = [vp, C.POINTER(RmStats)]
+    lib.rm_reset_stats.argtypes = [vp]
+    _lib = lib
+    return lib

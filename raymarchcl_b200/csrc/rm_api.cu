@@ -1,0 +1,526 @@
+// rm_api.cu -- the C ABI of libraymarch_b200.so (include/raymarch_b200.h).
+// Replaces the simplecl/JOCL pipeline of /root/reference/src/thi/ng/raymarchcl/core.clj:76-148.
+#include "../../include/raymarch_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rm_kernels.h"
+#include "rm_types.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind = 0;  // 0 render, 1 tonemap, 2 h2d, 3 d2h
+};
+
+}  // namespace
+
+struct rm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;      // stream in use
+  cudaStream_t own_stream = nullptr;  // the context's own stream
+  std::string err;
+
+  // volume ("v-buf")
+  uint8_t* d_vox = nullptr;
+  int rx = 0, ry = 0, rz = 0;
+
+  // framebuffer ("p-buf", "q-buf")
+  float4* d_accum = nullptr;
+  uint32_t* d_argb = nullptr;
+  int W = 0, H = 0;
+  size_t fb_capacity = 0;  // pixels allocated
+
+  // per-pass inputs
+  float4* d_tables = nullptr;  // resident scatter tables, 16384 float4 each
+  int table_capacity = 0;
+  std::vector<RmOpts> passes;  // decoded resident opts
+  int resident = 0;            // passes uploaded by rm_upload_passes
+
+  // pinned staging
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+
+  RmShard shard{};
+  int shard_rank = 0, shard_world = 1, shard_tw = 32, shard_th = 32;
+
+  RmCounters* d_counters = nullptr;
+  int count_work = 0;
+  int kernel_kind = 0;
+
+  rm_stats stats{};
+  std::vector<EventPair> pending, free_events;
+};
+
+namespace {
+
+int fail(rm_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int cuda_fail(rm_ctx* ctx, cudaError_t e, const char* what) {
+  return fail(ctx, RM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define RM_CUDA(ctx, call)                                  \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+  } while (0)
+
+float rd_f(const uint8_t* b, int off) { float f; std::memcpy(&f, b + off, 4); return f; }
+int rd_i(const uint8_t* b, int off) { int32_t i; std::memcpy(&i, b + off, 4); return i; }
+float3 rd_f3(const uint8_t* b, int off) { return make_float3(rd_f(b, off), rd_f(b, off + 4), rd_f(b, off + 8)); }
+
+// TRenderOpts blob -> RmOpts. Offsets: OpenCL layout of renderer.cl:35-78 (float3/int3 = 16 B).
+void decode_opts(const void* blob, RmOpts* o) {
+  const uint8_t* b = static_cast<const uint8_t*>(blob);
+  o->eyePos = rd_f3(b, 0);          o->targetPos = rd_f3(b, 16);   o->up = rd_f3(b, 32);
+  o->voxelBounds = rd_f3(b, 48);    o->voxelBounds2 = rd_f3(b, 64);
+  o->boundsMin = rd_f3(b, 80);      o->boundsMax = rd_f3(b, 96);
+  o->invVoxelScale = rd_f3(b, 112); o->sky1 = rd_f3(b, 128);       o->sky2 = rd_f3(b, 144);
+  o->rx = rd_i(b, 160); o->ry = rd_i(b, 164); o->rz = rd_i(b, 168); o->rxy = rd_i(b, 172);
+  o->width = rd_i(b, 176); o->height = rd_i(b, 180);
+  o->invAspect = rd_f(b, 184); o->time = rd_f(b, 188); o->fov = rd_f(b, 192);
+  o->maxIter = rd_i(b, 196); o->maxVoxelIter = rd_i(b, 200);
+  o->maxDist = rd_f(b, 204); o->startDist = rd_f(b, 208); o->eps = rd_f(b, 212);
+  o->aoIter = rd_i(b, 216);
+  o->aoStepDist = rd_f(b, 220); o->aoAmp = rd_f(b, 224); o->voxelSize = rd_f(b, 228);
+  o->groundY = rd_f(b, 232);
+  o->shadowIter = rd_i(b, 236); o->reflectIter = rd_i(b, 240);
+  o->shadowBias = rd_f(b, 244); o->lightScatter = rd_f(b, 248); o->minLightAtt = rd_f(b, 252);
+  o->gamma = rd_f(b, 256); o->exposure = rd_f(b, 260); o->dof = rd_f(b, 264);
+  o->frameBlend = rd_f(b, 268); o->fogPow = rd_f(b, 272); o->flareAmp = rd_f(b, 276);
+  o->isoVal = b[284]; o->numLights = b[285];
+  for (int i = 0; i < 4; ++i) {
+    o->lightPos[i] = rd_f3(b, 288 + 16 * i);
+    o->lightColor[i] = rd_f3(b, 352 + 16 * i);
+    o->mat[i].albedo = rd_f3(b, 416 + 32 * i);
+    o->mat[i].r0 = rd_f(b, 416 + 32 * i + 16);
+    o->mat[i].smoothness = rd_f(b, 416 + 32 * i + 20);
+  }
+}
+
+int check_opts(rm_ctx* ctx, const RmOpts& o) {
+  char msg[256];
+  if (o.rx != ctx->rx || o.ry != ctx->ry || o.rz != ctx->rz || o.rxy != ctx->rx * ctx->ry) {
+    std::snprintf(msg, sizeof msg, "TRenderOpts.voxelRes (%d,%d,%d,%d) does not match the uploaded volume %dx%dx%d",
+                  o.rx, o.ry, o.rz, o.rxy, ctx->rx, ctx->ry, ctx->rz);
+    return fail(ctx, RM_ERR_BAD_OPTS, msg);
+  }
+  if (o.width != ctx->W || o.height != ctx->H) {
+    std::snprintf(msg, sizeof msg, "TRenderOpts.resolution (%d,%d) does not match the framebuffer %dx%d",
+                  o.width, o.height, ctx->W, ctx->H);
+    return fail(ctx, RM_ERR_BAD_OPTS, msg);
+  }
+  if (o.numLights > 4) return fail(ctx, RM_ERR_BAD_OPTS, "TRenderOpts.numLights > 4");
+  if (o.maxVoxelIter < 0 || o.maxIter < 0 || o.shadowIter < 0)
+    return fail(ctx, RM_ERR_BAD_OPTS, "TRenderOpts iteration limits must be >= 0");
+  return RM_OK;
+}
+
+void update_shard(rm_ctx* c) {
+  RmShard& s = c->shard;
+  s.rank = c->shard_rank; s.world = c->shard_world;
+  s.tile_w = c->shard_tw; s.tile_h = c->shard_th;
+  s.tiles_x = c->W > 0 ? (c->W + s.tile_w - 1) / s.tile_w : 0;
+  s.tiles_y = c->H > 0 ? (c->H + s.tile_h - 1) / s.tile_h : 0;
+  const long long tiles = (long long)s.tiles_x * s.tiles_y;
+  s.owned_tiles = tiles > s.rank ? (int)((tiles - s.rank + s.world - 1) / s.world) : 0;
+  s.slots = (long long)s.owned_tiles * s.tile_w * s.tile_h;
+}
+
+int ensure_stage(rm_ctx* c, size_t bytes) {
+  if (c->h_stage_bytes >= bytes) return RM_OK;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr; c->h_stage_bytes = 0;
+  RM_CUDA(c, cudaMallocHost(&c->h_stage, bytes));
+  c->h_stage_bytes = bytes;
+  return RM_OK;
+}
+
+int ensure_tables(rm_ctx* c, int n) {
+  if (c->table_capacity >= n) return RM_OK;
+  if (c->d_tables) cudaFree(c->d_tables);
+  c->d_tables = nullptr; c->table_capacity = 0;
+  RM_CUDA(c, cudaMalloc(&c->d_tables, (size_t)n * RM_TABLE_FLOATS * sizeof(float)));
+  c->table_capacity = n;
+  return RM_OK;
+}
+
+EventPair begin_timed(rm_ctx* c, int kind) {
+  EventPair p;
+  if (!c->free_events.empty()) { p = c->free_events.back(); c->free_events.pop_back(); }
+  else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+  p.kind = kind;
+  cudaEventRecord(p.a, c->stream);
+  return p;
+}
+void end_timed(rm_ctx* c, EventPair p) {
+  cudaEventRecord(p.b, c->stream);
+  c->pending.push_back(p);
+}
+void resolve_timers(rm_ctx* c) {
+  for (EventPair& p : c->pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      switch (p.kind) {
+        case 0: c->stats.render_ms += ms; break;
+        case 1: c->stats.tonemap_ms += ms; break;
+        case 2: c->stats.h2d_ms += ms; break;
+        default: c->stats.d2h_ms += ms; break;
+      }
+    }
+    c->free_events.push_back(p);
+  }
+  c->pending.clear();
+}
+
+int launch_pass(rm_ctx* c, const RmOpts& o, const float4* d_table) {
+  EventPair t = begin_timed(c, 0);
+  cudaError_t e;
+  RmCounters* cnt = c->count_work ? c->d_counters : nullptr;
+  e = rm_launch_render_plain(c->d_vox, d_table, o, c->shard, c->d_accum, cnt, c->stream);
+  end_timed(c, t);
+  if (e != cudaSuccess) return cuda_fail(c, e, "render kernel launch");
+  c->stats.kernel_launches += 1;
+  c->stats.pixel_samples += (uint64_t)rm_shard_pixels(c);
+  if (c->pending.size() > 512) resolve_timers(c);
+  return RM_OK;
+}
+
+int require_ready(rm_ctx* c) {
+  if (!c->d_vox) return fail(c, RM_ERR_NO_VOLUME, "no volume uploaded (rm_set_volume)");
+  if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  return RM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rm_abi_version(void) { return RM_ABI_VERSION; }
+
+int rm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* rm_last_error(const rm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rm_create(int device_id, rm_ctx** out_ctx) {
+  if (!out_ctx) return fail(nullptr, RM_ERR_INVALID_ARG, "rm_create: out_ctx is null");
+  *out_ctx = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, RM_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  }
+  if (device_id < 0 || device_id >= n) return fail(nullptr, RM_ERR_INVALID_ARG, "rm_create: device_id out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    char msg[160];
+    std::snprintf(msg, sizeof msg, "device %d (%s) is sm_%d%d; this library carries sm_100a code only",
+                  device_id, prop.name, prop.major, prop.minor);
+    return fail(nullptr, RM_ERR_NO_DEVICE, msg);
+  }
+  rm_ctx* c = new (std::nothrow) rm_ctx();
+  if (!c) return fail(nullptr, RM_ERR_INVALID_ARG, "out of host memory");
+  c->device = device_id;
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_counters, sizeof(RmCounters))) != cudaSuccess ||
+      (e = cudaMemset(c->d_counters, 0, sizeof(RmCounters))) != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e, "rm_create");
+    delete c;
+    return rc;
+  }
+  c->stream = c->own_stream;
+  update_shard(c);
+  *out_ctx = c;
+  return RM_OK;
+}
+
+void rm_destroy(rm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  resolve_timers(c);
+  for (EventPair& p : c->free_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_tables); cudaFree(c->d_counters);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int rm_set_volume(rm_ctx* c, const uint8_t* voxels, int rx, int ry, int rz) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!voxels || rx <= 0 || ry <= 0 || rz <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: null volume or non-positive extent");
+  if ((long long)rx * ry > 0x7fffffffLL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: rx*ry overflows int (voxelRes.w)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)rx * ry * rz;
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; }
+  RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
+  EventPair t = begin_timed(c, 2);
+  cudaError_t e = cudaMemcpyAsync(c->d_vox, voxels, bytes, cudaMemcpyHostToDevice, c->stream);
+  end_timed(c, t);
+  if (e != cudaSuccess) return cuda_fail(c, e, "volume upload");
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stats.h2d_bytes += bytes;
+  c->rx = rx; c->ry = ry; c->rz = rz;
+  return RM_OK;
+}
+
+int rm_clear_accum(rm_ctx* c, int width, int height) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL / 37)
+    return fail(c, RM_ERR_INVALID_ARG, "rm_clear_accum: bad framebuffer extent");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)width * height;
+  if (n > c->fb_capacity) {
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_accum); cudaFree(c->d_argb);
+    c->d_accum = nullptr; c->d_argb = nullptr; c->fb_capacity = 0;
+    RM_CUDA(c, cudaMalloc(&c->d_accum, n * sizeof(float4)));
+    RM_CUDA(c, cudaMalloc(&c->d_argb, n * sizeof(uint32_t)));
+    c->fb_capacity = n;
+  }
+  c->W = width; c->H = height;
+  update_shard(c);
+  RM_CUDA(c, cudaMemsetAsync(c->d_accum, 0, n * sizeof(float4), c->stream));
+  return RM_OK;
+}
+
+int rm_render_pass(rm_ctx* c, const void* opts, size_t opts_len, const float* mc, size_t mc_floats) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!opts || opts_len != RM_OPTS_BYTES) return fail(c, RM_ERR_INVALID_ARG, "rm_render_pass: opts must be a 544-byte TRenderOpts blob");
+  if (!mc || mc_floats != RM_TABLE_FLOATS) return fail(c, RM_ERR_INVALID_ARG, "rm_render_pass: mc must hold 65536 floats (16384 float4)");
+  const void* o[1] = {opts};
+  const float* m[1] = {mc};
+  return rm_render_frame(c, o, m, 1);
+}
+
+int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!opts || !mc || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_render_frame: null arrays or iter <= 0");
+  int rc = require_ready(c);
+  if (rc) return rc;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  std::vector<RmOpts> dec((size_t)iter);
+  for (int i = 0; i < iter; ++i) {
+    if (!opts[i] || !mc[i]) return fail(c, RM_ERR_INVALID_ARG, "rm_render_frame: null per-pass pointer");
+    decode_opts(opts[i], &dec[i]);
+    if ((rc = check_opts(c, dec[i]))) return rc;
+  }
+  const size_t tbytes = (size_t)RM_TABLE_FLOATS * sizeof(float);
+  if ((rc = ensure_tables(c, iter > c->resident ? iter : c->resident))) return rc;
+  if ((rc = ensure_stage(c, tbytes * iter))) return rc;
+  // a frame rendered from host buffers replaces any resident passes
+  c->resident = 0;
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));  // staging buffer reuse
+  for (int i = 0; i < iter; ++i) std::memcpy(static_cast<char*>(c->h_stage) + tbytes * i, mc[i], tbytes);
+  EventPair t = begin_timed(c, 2);
+  cudaError_t e = cudaMemcpyAsync(c->d_tables, c->h_stage, tbytes * iter, cudaMemcpyHostToDevice, c->stream);
+  end_timed(c, t);
+  if (e != cudaSuccess) return cuda_fail(c, e, "table upload");
+  c->stats.h2d_bytes += tbytes * iter + (size_t)RM_OPTS_BYTES * iter;
+  for (int i = 0; i < iter; ++i)
+    if ((rc = launch_pass(c, dec[i], c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4)))) return rc;
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RM_OK;
+}
+
+int rm_upload_passes(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!opts || !mc || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: null arrays or iter <= 0");
+  int rc = require_ready(c);
+  if (rc) return rc;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  std::vector<RmOpts> dec((size_t)iter);
+  for (int i = 0; i < iter; ++i) {
+    if (!opts[i] || !mc[i]) return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: null per-pass pointer");
+    decode_opts(opts[i], &dec[i]);
+    if ((rc = check_opts(c, dec[i]))) return rc;
+  }
+  const size_t tbytes = (size_t)RM_TABLE_FLOATS * sizeof(float);
+  if ((rc = ensure_tables(c, iter))) return rc;
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < iter; ++i)
+    RM_CUDA(c, cudaMemcpyAsync(c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4), mc[i], tbytes, cudaMemcpyHostToDevice, c->stream));
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stats.h2d_bytes += (tbytes + RM_OPTS_BYTES) * iter;
+  c->passes = dec;
+  c->resident = iter;
+  return RM_OK;
+}
+
+int rm_render_resident(rm_ctx* c, int first, int count) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  int rc = require_ready(c);
+  if (rc) return rc;
+  if (first < 0 || count <= 0 || first + count > c->resident)
+    return fail(c, RM_ERR_INVALID_ARG, "rm_render_resident: pass range outside the uploaded passes");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  for (int i = first; i < first + count; ++i) {
+    if ((rc = check_opts(c, c->passes[i]))) return rc;
+    if ((rc = launch_pass(c, c->passes[i], c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4)))) return rc;
+  }
+  return RM_OK;
+}
+
+int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!opts || opts_len != RM_OPTS_BYTES || !argb_out) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap: bad opts blob or null output");
+  if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RmOpts o;
+  decode_opts(opts, &o);
+  if (o.width != c->W || o.height != c->H) return fail(c, RM_ERR_BAD_OPTS, "rm_tonemap: TRenderOpts.resolution does not match the framebuffer");
+  const size_t n = (size_t)c->W * c->H;
+  int rc = ensure_stage(c, n * sizeof(uint32_t));
+  if (rc) return rc;
+  EventPair t = begin_timed(c, 1);
+  cudaError_t e = rm_launch_tonemap(c->d_accum, o.gamma, c->W, c->H, c->shard, c->d_argb, 0, c->stream);
+  end_timed(c, t);
+  if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
+  c->stats.kernel_launches += 1;
+  EventPair t2 = begin_timed(c, 3);
+  e = cudaMemcpyAsync(c->h_stage, c->d_argb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  end_timed(c, t2);
+  if (e != cudaSuccess) return cuda_fail(c, e, "argb read-back");
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::memcpy(argb_out, c->h_stage, n * sizeof(uint32_t));
+  c->stats.d2h_bytes += n * sizeof(uint32_t);
+  return RM_OK;
+}
+
+int rm_tonemap_device(rm_ctx* c, const void* opts, size_t opts_len, void* d_argb, int packed) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!opts || opts_len != RM_OPTS_BYTES || !d_argb) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap_device: bad opts blob or null output");
+  if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RmOpts o;
+  decode_opts(opts, &o);
+  if (o.width != c->W || o.height != c->H) return fail(c, RM_ERR_BAD_OPTS, "rm_tonemap_device: TRenderOpts.resolution does not match the framebuffer");
+  EventPair t = begin_timed(c, 1);
+  cudaError_t e = rm_launch_tonemap(c->d_accum, o.gamma, c->W, c->H, c->shard, static_cast<uint32_t*>(d_argb), packed, c->stream);
+  end_timed(c, t);
+  if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
+  c->stats.kernel_launches += 1;
+  return RM_OK;
+}
+
+int rm_copy_accum_device(rm_ctx* c, void* d_rgba, int packed) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!d_rgba) return fail(c, RM_ERR_INVALID_ARG, "rm_copy_accum_device: null output");
+  if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  if (packed) {
+    cudaError_t e = rm_launch_pack_accum(c->d_accum, c->W, c->H, c->shard, static_cast<float4*>(d_rgba), c->stream);
+    if (e != cudaSuccess) return cuda_fail(c, e, "pack kernel launch");
+    c->stats.kernel_launches += 1;
+  } else {
+    RM_CUDA(c, cudaMemcpyAsync(d_rgba, c->d_accum, (size_t)c->W * c->H * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return RM_OK;
+}
+
+int rm_read_accum(rm_ctx* c, float* rgba_out) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!rgba_out) return fail(c, RM_ERR_INVALID_ARG, "rm_read_accum: null output");
+  if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->W * c->H * sizeof(float4);
+  RM_CUDA(c, cudaMemcpyAsync(rgba_out, c->d_accum, bytes, cudaMemcpyDeviceToHost, c->stream));
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stats.d2h_bytes += bytes;
+  return RM_OK;
+}
+
+int rm_sync(rm_ctx* c) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RM_OK;
+}
+
+int rm_set_stream(rm_ctx* c, void* cuda_stream) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  resolve_timers(c);
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return RM_OK;
+}
+
+int rm_set_tile_shard(rm_ctx* c, int rank, int world, int tile_w, int tile_h) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (world <= 0 || rank < 0 || rank >= world || tile_w <= 0 || tile_h <= 0 || (tile_w & 7) || (tile_h & 3))
+    return fail(c, RM_ERR_INVALID_ARG, "rm_set_tile_shard: need 0 <= rank < world, tile_w % 8 == 0, tile_h % 4 == 0");
+  c->shard_rank = rank; c->shard_world = world; c->shard_tw = tile_w; c->shard_th = tile_h;
+  update_shard(c);
+  return RM_OK;
+}
+
+int64_t rm_shard_pixels(const rm_ctx* c) {
+  if (!c || c->W <= 0) return 0;
+  const RmShard& s = c->shard;
+  int64_t px = 0;
+  for (long long lt = 0; lt < s.owned_tiles; ++lt) {
+    const long long t = lt * s.world + s.rank;
+    const int ty = (int)(t / s.tiles_x), tx = (int)(t % s.tiles_x);
+    const int w = (tx + 1) * s.tile_w <= c->W ? s.tile_w : c->W - tx * s.tile_w;
+    const int h = (ty + 1) * s.tile_h <= c->H ? s.tile_h : c->H - ty * s.tile_h;
+    px += (int64_t)w * h;
+  }
+  return px;
+}
+
+int rm_set_option(rm_ctx* c, int option, int64_t value) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  switch (option) {
+    case RM_OPT_COUNT_WORK: c->count_work = value != 0; return RM_OK;
+    case RM_OPT_KERNEL:
+      if (value < 0 || value > 1) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_KERNEL: 0 (fast) or 1 (plain)");
+      c->kernel_kind = (int)value;
+      return RM_OK;
+    default: return fail(c, RM_ERR_UNSUPPORTED, "rm_set_option: unknown option");
+  }
+}
+
+int rm_get_stats(const rm_ctx* cc, rm_stats* out) {
+  rm_ctx* c = const_cast<rm_ctx*>(cc);
+  if (!c || !out) return RM_ERR_INVALID_ARG;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  resolve_timers(c);
+  RmCounters h{};
+  RM_CUDA(c, cudaMemcpy(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+  c->stats.steps = h.steps; c->stats.taps = h.taps; c->stats.outer_iters = h.outer;
+  *out = c->stats;
+  return RM_OK;
+}
+
+int rm_reset_stats(rm_ctx* c) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  resolve_timers(c);
+  RM_CUDA(c, cudaMemset(c->d_counters, 0, sizeof(RmCounters)));
+  c->stats = rm_stats{};
+  return RM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// rm_kernels.cu -- device code of the render op for sm_100a.
+// Compiled with -fmad=false: geometry must follow the pinned two-rounding evaluation order
+// (DESIGN.md "Numerics"), and the shading code shares the translation unit.
+#include "rm_kernels.h"
+#include "rm_scene_plain.cuh"
+
+namespace {
+
+constexpr int kPlainBlock = 128;
+
+// RenderImage (renderer.cl:478-494), plain form: one thread per work slot.
+template <bool kCount>
+__global__ void __launch_bounds__(kPlainBlock)
+k_render_plain(const uint8_t* __restrict__ vox, const float4* __restrict__ table,
+               const __grid_constant__ RmOpts o, const __grid_constant__ RmShard sh,
+               float4* __restrict__ accum, RmCounters* __restrict__ counters) {
+  const long long slot = (long long)blockIdx.x * kPlainBlock + threadIdx.x;
+  plain::Scene s(vox, table, o);
+  if (slot < sh.slots) {
+    const int id = rm_slot_to_pixel(sh, slot, o.width, o.height);
+    if (id >= 0) {
+      const float3 c = plain::render_pixel_sample(s, id);
+      const float4 old = accum[id];
+      const float3 m = lerp3(f3(old.x, old.y, old.z), c, o.frameBlend);  // mix(), renderer.cl:492
+      accum[id] = make_float4(m.x, m.y, m.z, 1.0f);
+    }
+  }
+  if (kCount) {
+    unsigned long long a = s.w.steps, b = s.w.taps, c = s.w.outer;
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, off);
+      b += __shfl_down_sync(0xffffffffu, b, off);
+      c += __shfl_down_sync(0xffffffffu, c, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&counters->steps, a);
+      atomicAdd(&counters->taps, b);
+      atomicAdd(&counters->outer, c);
+    }
+  }
+}
+
+// tonemap + pack of one pixel (renderer.cl:448-454, :502-506)
+__device__ __forceinline__ uint32_t tonemap_pack(float4 p, float gamma) {
+  float c[3] = {p.x, p.y, p.z};
+  uint32_t ch[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float t = c[i] / (gamma + c[i]);
+    t = t * t * 255.0f;
+    ch[i] = (uint32_t)f2i_sat(cl_clamp(t, 0.0f, 255.0f));
+  }
+  return 0xff000000u | (ch[0] << 16) | (ch[1] << 8) | ch[2];
+}
+
+__global__ void __launch_bounds__(256)
+k_tonemap_linear(const float4* __restrict__ accum, float gamma, int n, uint32_t* __restrict__ argb) {
+  const int id = blockIdx.x * 256 + threadIdx.x;
+  if (id < n) argb[id] = tonemap_pack(accum[id], gamma);
+}
+
+__global__ void __launch_bounds__(256)
+k_tonemap_packed(const float4* __restrict__ accum, float gamma, int W, int H,
+                 const __grid_constant__ RmShard sh, uint32_t* __restrict__ argb) {
+  const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (slot >= sh.slots) return;
+  const int id = rm_slot_to_pixel(sh, slot, W, H);
+  argb[slot] = id >= 0 ? tonemap_pack(accum[id], gamma) : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_accum(const float4* __restrict__ accum, int W, int H, const __grid_constant__ RmShard sh,
+             float4* __restrict__ packed) {
+  const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (slot >= sh.slots) return;
+  const int id = rm_slot_to_pixel(sh, slot, W, H);
+  packed[slot] = id >= 0 ? accum[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+}  // namespace
+
+cudaError_t rm_launch_render_plain(const uint8_t* d_vox, const float4* d_table, const RmOpts& opts,
+                                   const RmShard& shard, float4* d_accum, RmCounters* d_counters,
+                                   cudaStream_t stream) {
+  if (shard.slots <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((shard.slots + kPlainBlock - 1) / kPlainBlock);
+  if (d_counters)
+    k_render_plain<true><<<blocks, kPlainBlock, 0, stream>>>(d_vox, d_table, opts, shard, d_accum, d_counters);
+  else
+    k_render_plain<false><<<blocks, kPlainBlock, 0, stream>>>(d_vox, d_table, opts, shard, d_accum, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t rm_launch_tonemap(const float4* d_accum, float gamma, int W, int H, const RmShard& shard,
+                              uint32_t* d_argb, int packed, cudaStream_t stream) {
+  if (packed) {
+    if (shard.slots <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((shard.slots + 255) / 256);
+    k_tonemap_packed<<<blocks, 256, 0, stream>>>(d_accum, gamma, W, H, shard, d_argb);
+  } else {
+    const int n = W * H;
+    k_tonemap_linear<<<(n + 255) / 256, 256, 0, stream>>>(d_accum, gamma, n, d_argb);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t rm_launch_pack_accum(const float4* d_accum, int W, int H, const RmShard& shard,
+                                 float4* d_packed, cudaStream_t stream) {
+  if (shard.slots <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((shard.slots + 255) / 256);
+  k_pack_accum<<<blocks, 256, 0, stream>>>(d_accum, W, H, shard, d_packed);
+  return cudaGetLastError();
+}

@@ -1,0 +1,35 @@
+// rm_kernels.h -- host-callable launchers of the device code (rm_kernels.cu), used by rm_api.cu.
+#pragma once
+#include "rm_types.h"
+
+// Maps a work slot of this shard to a pixel id (or -1 for padding of edge tiles). Slots are
+// tile-major; inside a tile consecutive groups of 32 slots cover 8x4 pixel blocks so that a warp
+// traces a compact bundle of primary rays.
+__host__ __device__ inline int rm_slot_to_pixel(const RmShard& sh, long long slot, int W, int H) {
+  const int tile_px = sh.tile_w * sh.tile_h;
+  const long long lt = slot / tile_px;
+  const int r = (int)(slot - lt * tile_px);
+  const long long t = lt * sh.world + sh.rank;
+  const int ty = (int)(t / sh.tiles_x), tx = (int)(t - (long long)ty * sh.tiles_x);
+  const int sb = r >> 5, l = r & 31;
+  const int sbw = sh.tile_w >> 3;
+  const int sby = sb / sbw, sbx = sb - sby * sbw;
+  const int x = tx * sh.tile_w + sbx * 8 + (l & 7);
+  const int y = ty * sh.tile_h + sby * 4 + (l >> 3);
+  if (x >= W || y >= H) return -1;
+  return y * W + x;
+}
+
+// RenderImage-equivalent, plain kernel (one thread per pixel-sample over the raw volume).
+cudaError_t rm_launch_render_plain(const uint8_t* d_vox, const float4* d_table, const RmOpts& opts,
+                                   const RmShard& shard, float4* d_accum, RmCounters* d_counters,
+                                   cudaStream_t stream);
+
+// TonemapImage-equivalent. packed == 0: d_argb[id] for every pixel of the frame (W*H words).
+// packed != 0: d_argb[slot] for the slots of this shard (shard.slots words, padding = 0).
+cudaError_t rm_launch_tonemap(const float4* d_accum, float gamma, int W, int H, const RmShard& shard,
+                              uint32_t* d_argb, int packed, cudaStream_t stream);
+
+// Accumulator gather into a packed, slot-ordered buffer (shard.slots float4, padding = 0).
+cudaError_t rm_launch_pack_accum(const float4* d_accum, int W, int H, const RmShard& shard,
+                                 float4* d_packed, cudaStream_t stream);

@@ -1,0 +1,38 @@
+// rm_math.cuh -- fp32 vector helpers with the evaluation order the reference's OpenCL built-ins
+// imply. This translation unit is compiled with -fmad=false so every a*b+c below is
+// two roundings, like mad() without -cl-mad-enable; division and sqrt are IEEE (nvcc defaults).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#define RM_DEV __device__ __forceinline__
+
+RM_DEV float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+RM_DEV float3 f3s(float s) { return make_float3(s, s, s); }
+RM_DEV float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RM_DEV float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RM_DEV float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RM_DEV float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+RM_DEV float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+RM_DEV float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
+RM_DEV float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+
+// OpenCL 6.12.4 common functions: min(x,y) = y<x?y:x, max(x,y) = x<y?y:x (NaN-order sensitive)
+RM_DEV float cl_min(float x, float y) { return y < x ? y : x; }
+RM_DEV float cl_max(float x, float y) { return x < y ? y : x; }
+RM_DEV float cl_clamp(float x, float lo, float hi) { return cl_min(cl_max(x, lo), hi); }
+RM_DEV float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RM_DEV float3 cross3(float3 a, float3 b) {
+  return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+RM_DEV float len3(float3 a) { return sqrtf(dot3(a, a)); }
+// normalize(0) = 0 (pinned)
+RM_DEV float3 unit3(float3 a) {
+  const float l = len3(a);
+  return l == 0.0f ? a : a / l;
+}
+RM_DEV float3 lerp3(float3 a, float3 b, float t) { return a + (b - a) * t; }
+// (uint)float with two's-complement wrap of the truncated value, also for negatives (8c-1)
+RM_DEV uint32_t f2u_wrap(float f) { return (uint32_t)(long long)f; }
+// convert_int_sat: truncate toward zero, saturate, NaN -> 0 (8c-3) == cvt.rzi.s32.f32
+RM_DEV int f2i_sat(float f) { return __float2int_rz(f); }

@@ -1,0 +1,55 @@
+// rm_types.h -- host/device types shared by the C-ABI layer and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define RM_TABLE_MASK 0x3fffu  // renderer.cl:143
+
+struct RmMaterial {  // TMaterial, renderer.cl:14-19 (dummy float2 dropped)
+  float3 albedo;
+  float r0, smoothness;
+};
+
+// TRenderOpts (renderer.cl:35-78) decoded from the 544-byte blob by rm_api.cu:decode_opts().
+struct RmOpts {
+  float3 eyePos, targetPos, up;
+  float3 voxelBounds, voxelBounds2, boundsMin, boundsMax, invVoxelScale;
+  float3 sky1, sky2;
+  int rx, ry, rz, rxy;
+  int width, height;
+  float invAspect, time, fov;
+  int maxIter, maxVoxelIter;
+  float maxDist, startDist, eps;
+  int aoIter;
+  float aoStepDist, aoAmp, voxelSize, groundY;
+  int shadowIter, reflectIter;
+  float shadowBias, lightScatter, minLightAtt, gamma, exposure, dof, frameBlend, fogPow, flareAmp;
+  int isoVal, numLights;
+  float3 lightPos[4], lightColor[4];
+  RmMaterial mat[4];
+};
+
+// Interleaved tile ownership: this context renders tiles t with t % world == rank.
+struct RmShard {
+  int rank, world;
+  int tile_w, tile_h;     // tile extent in pixels (multiples of 8 x 4)
+  int tiles_x, tiles_y;   // tile grid over the framebuffer
+  int owned_tiles;        // tiles owned by this rank
+  long long slots;        // owned_tiles * tile_w * tile_h (includes padding of edge tiles)
+};
+
+struct RmCounters {  // reference-equivalent work, see rm_stats in raymarch_b200.h
+  unsigned long long steps, taps, outer;
+};
+
+// Occupancy acceleration data derived from the volume for one isoVal (built by rm_build_accel).
+struct RmAccel {
+  const uint8_t* vox;         // the uploaded volume, x fastest
+  const uint64_t* solid;      // bit-bricks of (v >  isoVal): one 64-bit word per 4x4x4 voxels
+  const uint64_t* occ;        // bit-bricks of (v >= isoVal)
+  const uint8_t* dist;        // per macro-cell Chebyshev distance (in macro-cells) to the nearest
+                              // macro-cell containing a solid voxel, saturated at 255; 0 = occupied
+  int bx, by, bz;             // brick grid extents  = ceil(res / 4)
+  int mx, my, mz;             // macro-cell grid extents = ceil(res / cell)
+  int cell_shift;             // macro-cell edge = 1 << cell_shift voxels
+};

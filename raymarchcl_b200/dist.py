@@ -1,0 +1,126 @@
+"""Multi-GPU plumbing of the render op: interleaved tile ownership + ONE framebuffer gather.
+
+The reference is single-device (core.clj:121-123). A work-item reads only read-only buffers and
+its own ``pixels[id]`` (renderer.cl:483-492), so the frame shards by pixels with no exchange until
+the end: every rank holds the whole volume and renders the tiles ``t % world == rank``
+(round-robin, because cost varies ~10x across the image), then the packed ARGB tiles are gathered
+to rank 0 in one collective (NCCL over NVLink under torchrun; gloo in the CPU tests) and
+de-interleaved into the frame. One process per GPU; ``torch.distributed`` is plumbing only.
+
+``slot_pixel_index`` is the host mirror of ``rm_slot_to_pixel`` (csrc/rm_kernels.h).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class ShardLayout:
+    width: int
+    height: int
+    world: int
+    tile_w: int = 32
+    tile_h: int = 32
+
+    @property
+    def tiles_x(self) -> int:
+        return (self.width + self.tile_w - 1) // self.tile_w
+
+    @property
+    def tiles_y(self) -> int:
+        return (self.height + self.tile_h - 1) // self.tile_h
+
+    @property
+    def tiles(self) -> int:
+        return self.tiles_x * self.tiles_y
+
+    def owned_tiles(self, rank: int) -> int:
+        return (self.tiles - rank + self.world - 1) // self.world if self.tiles > rank else 0
+
+    def slots(self, rank: int) -> int:
+        return self.owned_tiles(rank) * self.tile_w * self.tile_h
+
+    @property
+    def max_slots(self) -> int:
+        return max(self.slots(r) for r in range(self.world))
+
+    def slot_pixel_index(self, rank: int) -> np.ndarray:
+        """int64[slots(rank)]: pixel id (y*W+x) of every work slot of ``rank``; -1 = edge padding."""
+        n = self.slots(rank)
+        slot = np.arange(n, dtype=np.int64)
+        tile_px = self.tile_w * self.tile_h
+        lt, r = slot // tile_px, slot % tile_px
+        t = lt * self.world + rank
+        ty, tx = t // self.tiles_x, t % self.tiles_x
+        sb, l = r >> 5, r & 31
+        sbw = self.tile_w >> 3
+        sby, sbx = sb // sbw, sb % sbw
+        x = tx * self.tile_w + sbx * 8 + (l & 7)
+        y = ty * self.tile_h + sby * 4 + (l >> 3)
+        pid = y * self.width + x
+        pid[(x >= self.width) | (y >= self.height)] = -1
+        return pid
+
+
+def assemble_frame(parts, layout: ShardLayout, out=None):
+    """De-interleave per-rank packed buffers (``parts[r][:slots(r)]``) into one flat frame of
+    ``width*height`` elements. Works on numpy arrays and torch tensors (any device)."""
+    import torch
+    first = parts[0]
+    is_torch = isinstance(first, torch.Tensor)
+    n = layout.width * layout.height
+    if out is None:
+        out = (torch.zeros((n,) + tuple(first.shape[1:]), dtype=first.dtype, device=first.device)
+               if is_torch else np.zeros((n,) + first.shape[1:], dtype=first.dtype))
+    for r in range(layout.world):
+        idx = layout.slot_pixel_index(r)
+        valid = idx >= 0
+        if is_torch:
+            ti = torch.from_numpy(idx[valid]).to(first.device)
+            tv = torch.from_numpy(np.nonzero(valid)[0]).to(first.device)
+            out[ti] = parts[r][tv]
+        else:
+            out[idx[valid]] = parts[r][: idx.size][valid]
+    return out
+
+
+class FrameGatherer:
+    """Precomputed index maps + buffers for the one gather of a frame to ``dst``."""
+
+    def __init__(self, layout: ShardLayout, rank: int, device, dtype, dst: int = 0, elem_shape=()):
+        import torch
+        self.layout, self.rank, self.dst = layout, rank, dst
+        self.max_slots = layout.max_slots
+        self.local = torch.zeros((self.max_slots,) + tuple(elem_shape), dtype=dtype, device=device)
+        self.parts: Optional[List] = None
+        self.frame = None
+        if rank == dst:
+            self.parts = [torch.zeros_like(self.local) for _ in range(layout.world)]
+            self.frame = torch.zeros((layout.width * layout.height,) + tuple(elem_shape), dtype=dtype, device=device)
+            # one fused scatter: concatenated source positions -> pixel ids
+            src, dstpix = [], []
+            for r in range(layout.world):
+                idx = layout.slot_pixel_index(r)
+                v = np.nonzero(idx >= 0)[0]
+                src.append(v + r * self.max_slots)
+                dstpix.append(idx[v])
+            self._src = torch.from_numpy(np.concatenate(src)).to(device)
+            self._dst = torch.from_numpy(np.concatenate(dstpix)).to(device)
+
+    def gather(self):
+        """Collective: every rank contributes ``self.local``; returns the flat frame on ``dst``."""
+        import torch
+        import torch.distributed as dist
+        if self.layout.world == 1:
+            stacked = self.local.unsqueeze(0)
+        else:
+            dist.gather(self.local, self.parts if self.rank == self.dst else None, dst=self.dst)
+            if self.rank != self.dst:
+                return None
+            stacked = torch.stack(self.parts)
+        flat = stacked.reshape((-1,) + tuple(self.local.shape[1:]))
+        self.frame[self._dst] = flat[self._src]
+        return self.frame
