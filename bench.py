@@ -1,0 +1,405 @@
+#!/usr/bin/env python3
+"""bench.py -- the render op's headline benchmark (BASELINE.json: Mray-steps/s and frames/s
+@1920x1080 16 passes on the 256^3 gyroid, `:metal` preset; % of HBM roofline).
+
+A "step" is one frame of the hot path: all RenderImage passes + TonemapImage (+ the one
+framebuffer gather when N > 1). One process per GPU (torchrun for N > 1); the frame is sharded by
+interleaved 32x32 tiles with no data-path collective until the final gather ("weak" is wrong for
+a fixed frame: total work is fixed, so `scaling` = "strong").
+
+  value     device-resident throughput: volume, tables and opts already in HBM; per-step CUDA
+            events on the launching stream, L2 flushed between steps, max over ranks.
+  e2e       the same frame through the reference-facing calls with HOST buffers every step:
+            rm_set_volume + rm_clear_accum + rm_render_frame + rm_tonemap (H2D of volume, tables,
+            opts and D2H of the ARGB frame inside the timed region), wall clock, max over ranks.
+  roofline  algorithmic bytes (1 B per reference-equivalent voxel fetch = inner steps + occupancy
+            taps) per launch of the render kernel / its CUDA-event duration,
+            against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  oracle/_ref (the reference's own kernel text, -O3 -ffast-math, OpenMP on all host
+            cores) on a bounded sample of the same frame. Checker code is only ever TIMED here.
+
+`--impl reference` times the reference's CPU implementation alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1] -- the configuration the metric is quoted on
+    "c2": dict(name="256^3 gyroid, 1920x1080, 16 passes, :metal, dof 0.001 (BASELINE configs[1])",
+               scene=dict(vres=256, width=1920, height=1080, iters=16, mat="metal")),
+    # the other configs are parity-test cases; selectable here for exploration only
+    "c1": dict(name="64^3 gyroid, 256x256, 1 pass, :ao (BASELINE configs[0])",
+               scene=dict(vres=64, width=256, height=256, iters=1, mat="ao")),
+    "c3": dict(name="512^3 blob stand-in, 1920x1080, 16 passes, :metal (BASELINE configs[2] stand-in)",
+               scene=dict(vres=512, width=1920, height=1080, iters=16, mat="metal", volume="blob")),
+    "c4": dict(name="256^3 gyroid, 3840x2160, 100 passes, :metal, dof 0.025 (BASELINE configs[3])",
+               scene=dict(vres=256, width=3840, height=2160, iters=100, mat="metal", dof=0.025)),
+    "c5": dict(name="1024^3 thin-blob stand-in, 1920x1080, 16 passes, :metal2 (BASELINE configs[4] stand-in)",
+               scene=dict(vres=1024, width=1920, height=1080, iters=16, mat="metal2", volume="dragon")),
+}
+TILE = (32, 32)
+L2_FLUSH_BYTES = 512 << 20  # > 126 MB L2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="fast", choices=["fast", "plain"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, taken from
+    the committed ncu capture summary (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))[f"{workload}:{kernel}"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(kind_pref=("ref_fast", "oracle")):
+    from oracle import build_oracle, refso
+    for k in kind_pref:
+        if k == "oracle":
+            build_oracle.build(verbose=False)
+        if refso.available(k):
+            r = refso.load(k)
+            return r, ("reference" if k.startswith("ref") else "port"), k
+    raise RuntimeError("no CPU reference library available")
+
+
+def cpu_sample_ids(width, height, stride):
+    return np.arange(0, width * height, stride, dtype=np.int32)
+
+
+def count_sample_steps(vol, mcs, opts, w, h, ids):
+    """Reference-equivalent work of the sample, counted by the strict checker (untimed)."""
+    from oracle import build_oracle, refso
+    build_oracle.build(verbose=False)
+    _, cnt = refso.load("oracle").render_frame(vol, mcs, opts, w, h, ids=ids)
+    return int(cnt[0]), int(cnt[1])
+
+
+def time_cpu(ref, vol, mcs, opts, w, h, ids):
+    t0 = time.perf_counter()
+    px, _ = ref.render_frame(vol, mcs, opts, w, h, ids=ids)
+    ref.tonemap(px, opts[0])
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref when it
+    was built from /root/reference, else the C port), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests.scenes import build_scene
+    wl = WORKLOADS[args.workload]
+    sc = wl["scene"]
+    w, h, iters = sc["width"], sc["height"], sc["iters"]
+    vol, opts, mcs = build_scene(**sc)
+    ref, kind, name = cpu_reference()
+    cores = host_threads()
+    ref.set_num_threads(cores)
+    stride = 16 if w * h * iters > 4_000_000 else 1
+    ids = cpu_sample_ids(w, h, stride)
+    steps_sample, taps_sample = count_sample_steps(vol, mcs, opts, w, h, ids)
+    for _ in range(args.warmup):
+        time_cpu(ref, vol, mcs, opts, w, h, ids)
+    ts = [time_cpu(ref, vol, mcs, opts, w, h, ids) for _ in range(args.steps)]
+    tot = sum(ts)
+    value = steps_sample * args.steps / tot / 1e6
+    sample = f"every {stride}th pixel id of all {iters} passes ({len(ids)} pixels, {steps_sample} inner steps per step)"
+    line = {
+        "impl": "reference", "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frames_per_s": value * 1e6 / (steps_sample * stride) if steps_sample else None,
+        "frames_per_s_note": "extrapolated from the sample by the step ratio",
+        "config": {"workload": wl["name"], "reference_build": name, "host": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from raymarchcl_b200 import _lib
+    from raymarchcl_b200.dist import FrameGatherer, ShardLayout
+    from raymarchcl_b200.renderer import Renderer
+    from tests.scenes import build_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the render op has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = WORKLOADS[args.workload]
+    sc = wl["scene"]
+    w, h, iters = sc["width"], sc["height"], sc["iters"]
+    vol, opts, mcs = build_scene(**sc)
+    vol_pinned = torch.from_numpy(np.ascontiguousarray(vol)).pin_memory()
+    vol_host = vol_pinned.numpy()
+
+    layout = ShardLayout(w, h, world, *TILE)
+    r = Renderer(local)
+    r.set_option(_lib.RM_OPT_KERNEL, 0 if args.kernel == "fast" else 1)
+    r.set_tile_shard(rank, world, *TILE)
+    stream = torch.cuda.Stream(device=dev)
+    r.set_stream(stream.cuda_stream)
+    gather = FrameGatherer(layout, rank, dev, torch.int32) if world > 1 else None
+    frame1 = torch.empty(w * h, dtype=torch.int32, device=dev) if world == 1 else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    argb_host = torch.empty(w * h, dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def resident_frame():
+        """all passes + tonemap (+ gather) from inputs resident in HBM; returns the frame on rank 0"""
+        r.clear_accum(w, h)
+        r.render_resident(0, iters)
+        if world == 1:
+            r.tonemap_device(opts[0], frame1.data_ptr(), packed=False)
+            return frame1
+        r.tonemap_device(opts[0], gather.local.data_ptr(), packed=True)
+        return gather.gather()
+
+    # ---- inputs into HBM, work count (untimed) ----
+    with torch.cuda.stream(stream):
+        r.set_volume(vol_host)
+        r.clear_accum(w, h)
+        r.upload_passes(opts, mcs)
+        r.reset_stats()
+        r.count_work(True)
+        resident_frame()
+        st = r.stats()
+        r.count_work(False)
+        work = torch.tensor([st["steps"], st["taps"], st["outer_iters"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(work)
+        steps_frame, taps_frame, outer_frame = [int(x) for x in work.tolist()]
+
+        # ---- device-resident timed loop ----
+        for _ in range(args.warmup):
+            resident_frame()
+            flush.zero_()
+        barrier()
+        r.reset_stats()
+        sampler = ClockSampler(local) if rank == 0 else None
+        t_wall0 = time.perf_counter()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ev:
+            a.record(stream)
+            resident_frame()
+            b.record(stream)
+            flush.zero_()  # L2 flush between timed iterations, outside the event pair
+        barrier()
+        t_wall1 = time.perf_counter()
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        st = r.stats()
+        t = torch.tensor([dev_ms, st["render_ms"]], dtype=torch.float64, device=dev)
+        launches = torch.tensor([st["kernel_launches"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches)
+        dev_ms, render_ms = t.tolist()
+
+        # ---- end to end through the host-buffer calls ----
+        e2e = None
+        if not args.no_e2e:
+            def host_frame():
+                r.set_volume(vol_host)
+                r.clear_accum(w, h)
+                r.render_frame(opts, mcs)
+                if world == 1:
+                    return r.tonemap(opts[0], out=argb_host.numpy().view(np.uint32))
+                r.tonemap_device(opts[0], gather.local.data_ptr(), packed=True)
+                fr = gather.gather()
+                if rank == 0:
+                    argb_host.copy_(fr, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                return None
+
+            for _ in range(max(1, min(args.warmup, 3))):
+                host_frame()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                host_frame()
+            barrier()
+            e2e_s = time.perf_counter() - t0
+            te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e_s = te.item()
+            h2d = vol.size + iters * (65536 * 4 + 544)
+            e2e = {"value": steps_frame * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s",
+                   "frames_per_s": args.steps / e2e_s, "ms_per_step": 1e3 * e2e_s / args.steps,
+                   "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(w * h * 4),
+                   "path": "rm_set_volume + rm_clear_accum + rm_render_frame + rm_tonemap, pinned host buffers"
+                           + ("" if world == 1 else "; every rank uploads its own copy of the inputs")}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = dev_ms / args.steps
+    value = steps_frame / (ms_per_step * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    # per launch of the render kernel: frame bytes / launches-per-frame over avg launch duration
+    kernel_s_per_frame = render_ms * 1e-3 / args.steps
+    achieved = (steps_frame / world + taps_frame / world) / kernel_s_per_frame / 1e9  # per GPU
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(args.workload, args.kernel),
+            "peak_source": peak_src,
+            "kernel": "k_render_fast (all passes of a frame in one launch)" if args.kernel == "fast"
+                      else "k_render_plain (one launch per pass)",
+            "algorithmic_bytes_per_frame": steps_frame + taps_frame,
+            "kernel_ms_per_frame": kernel_s_per_frame * 1e3,
+            "kernel_share_of_step": kernel_s_per_frame * 1e3 / ms_per_step,
+            "note": "1 B per reference-equivalent voxel fetch (inner steps + occupancy taps); the 16 MiB "
+                    "volume is L2-resident, so DRAM traffic is far below the algorithmic bytes by design"}
+
+    line = {
+        "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "frames_per_s": 1e3 / ms_per_step,
+        "config": {"workload": wl["name"], "kernel": args.kernel, "tile": list(TILE),
+                   "sharding": f"interleaved tiles over {world} GPU(s), one gather of packed ARGB to rank 0",
+                   "l2": "flushed between timed steps (512 MiB memset outside the event pair)",
+                   "steps_per_frame": steps_frame, "taps_per_frame": taps_frame,
+                   "outer_iters_per_frame": outer_frame, "pixel_samples_per_frame": w * h * iters},
+        "roofline": roof,
+        "e2e": e2e,
+        "gpu_launches": int(launches.item()),
+        "clocks": clocks,
+        "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ref, kind, name = cpu_reference()
+            cores = host_threads()
+            ref.set_num_threads(cores)
+            stride = 4 if w * h * iters > 4_000_000 else 1
+            ids = cpu_sample_ids(w, h, stride)
+            s_steps, _ = count_sample_steps(vol, mcs, opts, w, h, ids)
+            tcpu = time_cpu(ref, vol, mcs, opts, w, h, ids)
+            line["cpu_baseline"] = {
+                "value": s_steps / tcpu / 1e6, "unit": "Mray-steps/s", "cores": cores, "kind": kind,
+                "build": name, "seconds": tcpu,
+                "sample": f"every {stride}th pixel id of all {iters} passes ({len(ids)} pixels, {s_steps} inner steps)"}
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

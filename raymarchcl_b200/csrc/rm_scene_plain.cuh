@@ -16,8 +16,9 @@ struct Scene {
   const uint8_t* __restrict__ vox;
   const float4* __restrict__ table;
   const RmOpts& o;
+  float time;  // TRenderOpts.time of the pass this thread renders (per lane in the fused kernel)
   Work w;
-  RM_DEV Scene(const uint8_t* v, const float4* t, const RmOpts& opts) : vox(v), table(t), o(opts) {
+  RM_DEV Scene(const uint8_t* v, const float4* t, const RmOpts& opts) : vox(v), table(t), o(opts), time(opts.time) {
     w.steps = w.taps = w.outer = 0;
   }
 };
@@ -130,7 +131,7 @@ RM_DEV float3 sky(const RmOpts& o, float3 d) { return lerp3(o.sky1, o.sky2, d.y 
 
 // renderer.cl:263-269
 RM_DEV float3 light_pos(const Scene& s, const PixelState& st, int i) {
-  const uint32_t seed = f2u_wrap(st.px * 1957.0f + st.py * 2173.0f + s.o.time * 4763.742f);
+  const uint32_t seed = f2u_wrap(st.px * 1957.0f + st.py * 2173.0f + s.time * 4763.742f);
   return table_xyz(s, seed) * s.o.lightScatter + s.o.lightPos[i];
 }
 
@@ -174,7 +175,7 @@ RM_DEV float blinn_phong(float smooth, float3 rd, float3 ldir, float3 n) {
 RM_DEV float ambient_occlusion(Scene& s, float3 pos, float3 n0) {
   const RmOpts& o = s.o;
   float ao = 1.0f, d = 0.0f;
-  uint32_t seed = f2u_wrap(pos.x * 3183.75f + pos.y * 1831.42f + pos.z * 2945.87f + o.time * 2671.918f);
+  uint32_t seed = f2u_wrap(pos.x * 3183.75f + pos.y * 1831.42f + pos.z * 2945.87f + s.time * 2671.918f);
   for (int i = 0; i <= o.aoIter && ao > 0.01f; ++i) {
     d += o.aoStepDist;
     seed += 37u;
@@ -267,8 +268,8 @@ RM_DEV float3 scene_color(Scene& s, const PixelState& st, float3 ro, float3 rd) 
 // renderer.cl:467-476 + :456-465
 RM_DEV float3 setup_pixel(const Scene& s, int id, PixelState& st) {
   const RmOpts& o = s.o;
-  const float4 a = table_at(s, (uint32_t)(id * 17) + f2u_wrap(o.time * 3141.3862f));
-  st.mcNormal = unit3(table_xyz(s, (uint32_t)(id * 37) + f2u_wrap(o.time * 1859.1467f)));
+  const float4 a = table_at(s, (uint32_t)(id * 17) + f2u_wrap(s.time * 3141.3862f));
+  st.mcNormal = unit3(table_xyz(s, (uint32_t)(id * 37) + f2u_wrap(s.time * 1859.1467f)));
   st.px = (float)(id % o.width) + a.z;
   st.py = (float)(id / o.width) + a.w;
   st.eye = f3(st.mcNormal.z, st.mcNormal.x, st.mcNormal.y) * o.dof + o.eyePos;

@@ -42,14 +42,30 @@ struct RmCounters {  // reference-equivalent work, see rm_stats in raymarch_b200
   unsigned long long steps, taps, outer;
 };
 
-// Occupancy acceleration data derived from the volume for one isoVal (built by rm_build_accel).
+#define RM_DIST_CAP 32  // saturation of the macro-cell distance map
+
+// Occupancy acceleration data derived from the volume for one isoVal (rm_accel.cu). It only tells
+// the fast kernel which voxel fetches of the reference's march have a known outcome.
 struct RmAccel {
-  const uint8_t* vox;         // the uploaded volume, x fastest
+  const uint8_t* vox;         // the uploaded volume, x fastest (material band of a hit voxel)
   const uint64_t* solid;      // bit-bricks of (v >  isoVal): one 64-bit word per 4x4x4 voxels
-  const uint64_t* occ;        // bit-bricks of (v >= isoVal)
-  const uint8_t* dist;        // per macro-cell Chebyshev distance (in macro-cells) to the nearest
-                              // macro-cell containing a solid voxel, saturated at 255; 0 = occupied
-  int bx, by, bz;             // brick grid extents  = ceil(res / 4)
+  const uint64_t* occ;        // bit-bricks of (v >= isoVal) (aliases `solid` when no voxel == isoVal)
+  const uint8_t* dist;        // per macro-cell Chebyshev distance (in cells) to the nearest cell
+                              // holding a solid voxel, saturated at RM_DIST_CAP; 0 = occupied
+  int bx, by, bz;             // brick grid extents = ceil(res / 4)
   int mx, my, mz;             // macro-cell grid extents = ceil(res / cell)
-  int cell_shift;             // macro-cell edge = 1 << cell_shift voxels
+  int cell_shift;             // macro-cell edge = 1 << cell_shift voxels (>= 2)
+};
+
+struct RmAccelStorage {  // owner of the device arrays behind an RmAccel view
+  RmAccel view{};
+  uint64_t* d_solid = nullptr;
+  uint64_t* d_occ = nullptr;
+  uint8_t* d_dist = nullptr;
+  uint8_t* d_tmp = nullptr;
+  unsigned* d_flag = nullptr;
+  size_t brick_capacity = 0, cell_capacity = 0;
+  int iso = -1;
+  bool valid = false;
+  int launches = 0;
 };

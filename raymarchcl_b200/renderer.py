@@ -112,8 +112,11 @@ class Renderer:
     def render_resident(self, first: int, count: int) -> None:
         self._check(self._lib.rm_render_resident(self._h, int(first), int(count)))
 
-    def tonemap(self, opts: bytes) -> np.ndarray:
-        out = np.empty((self.height, self.width), dtype=np.uint32)
+    def tonemap(self, opts: bytes, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width), dtype=np.uint32)
+        elif out.dtype != np.uint32 or out.size != self.width * self.height or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous uint32 array of width*height words")
         self._check(self._lib.rm_tonemap(self._h, C.c_char_p(opts), len(opts), out.ctypes.data))
         return out
 
