@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", default="fast", choices=["fast", "plain"])
+    ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE",
+                    help="rm_set_option tuning knob of the fast kernel (results do not depend on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -235,6 +237,9 @@ def run_b200(args):
     layout = ShardLayout(w, h, world, *TILE)
     r = Renderer(local)
     r.set_option(_lib.RM_OPT_KERNEL, 0 if args.kernel == "fast" else 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        r.set_option(int(k), int(v))
     r.set_tile_shard(rank, world, *TILE)
     stream = torch.cuda.Stream(device=dev)
     r.set_stream(stream.cuda_stream)
@@ -361,7 +366,7 @@ def run_b200(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "frames_per_s": 1e3 / ms_per_step,
-        "config": {"workload": wl["name"], "kernel": args.kernel, "tile": list(TILE),
+        "config": {"workload": wl["name"], "kernel": args.kernel, "knobs": args.opt, "tile": list(TILE),
                    "sharding": f"interleaved tiles over {world} GPU(s), one gather of packed ARGB to rank 0",
                    "l2": "flushed between timed steps (512 MiB memset outside the event pair)",
                    "steps_per_frame": steps_frame, "taps_per_frame": taps_frame,

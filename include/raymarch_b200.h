@@ -60,6 +60,7 @@ typedef struct rm_stats {
   uint64_t outer_iters;
   uint64_t pixel_samples;   /* pixels x passes rendered */
   uint64_t kernel_launches; /* CUDA kernels launched by this context */
+  uint64_t render_launches; /* ... of which RenderImage-equivalent kernels (render_ms covers these) */
   double   render_ms;       /* device time of RenderImage-equivalent kernels (CUDA events) */
   double   tonemap_ms;      /* device time of TonemapImage-equivalent kernels */
   double   h2d_ms, d2h_ms;  /* device time of copies issued by this context */
@@ -68,7 +69,14 @@ typedef struct rm_stats {
 
 typedef enum rm_option {
   RM_OPT_COUNT_WORK = 1,   /* 0 (default) | 1: gather reference-equivalent work counters */
-  RM_OPT_KERNEL = 2        /* 0 = default fast kernel; 1 = plain one-thread-per-pixel kernel */
+  RM_OPT_KERNEL = 2,       /* 0 = default fast kernel; 1 = plain one-thread-per-pixel kernel */
+  /* tuning knobs of the fast kernel; none of them changes results */
+  RM_OPT_CELL_SHIFT = 3,   /* macro-cell edge of the distance map = 1<<value voxels; 0 = auto (~res/64) */
+  RM_OPT_MARCH_QUOTA = 4,  /* march iterations per trip round the lane state machine */
+  RM_OPT_MIN_MARCHERS = 5, /* leave the march loop when fewer lanes of the warp are marching */
+  RM_OPT_FUSE_LIMIT = 6,   /* max passes rendered by one launch (1..32) */
+  RM_OPT_TRIP_LIMIT = 7    /* watchdog: state-machine trips a warp may take per launch before the
+                              launch is abandoned with RM_ERR_CUDA (default 2^28) */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */
@@ -123,6 +131,8 @@ int64_t rm_shard_pixels(const rm_ctx* ctx);
 int rm_set_option(rm_ctx* ctx, int option, int64_t value);
 int rm_get_stats(const rm_ctx* ctx, rm_stats* out);
 int rm_reset_stats(rm_ctx* ctx);
+/* Diagnostic: the 32 watchdog / debug words of the render kernel (see RM_OPT_TRIP_LIMIT). */
+int rm_debug_read(rm_ctx* ctx, uint32_t* out32);
 
 #ifdef __cplusplus
 }

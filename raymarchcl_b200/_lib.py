@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libraymarch_b200.so")
+LIB_PATH = os.environ.get("RAYMARCH_B200_LIB") or os.path.join(PKG_DIR, "libraymarch_b200.so")
 
 OPTS_BYTES = 544
 TABLE_FLOATS = 65536
@@ -19,6 +19,11 @@ STATUS_NAMES = {0: "RM_OK", -1: "RM_ERR_INVALID_ARG", -2: "RM_ERR_BAD_OPTS", -3:
                 -4: "RM_ERR_NO_FRAMEBUFFER", -5: "RM_ERR_CUDA", -6: "RM_ERR_NO_DEVICE", -7: "RM_ERR_UNSUPPORTED"}
 RM_OPT_COUNT_WORK = 1
 RM_OPT_KERNEL = 2
+RM_OPT_CELL_SHIFT = 3
+RM_OPT_MARCH_QUOTA = 4
+RM_OPT_MIN_MARCHERS = 5
+RM_OPT_FUSE_LIMIT = 6
+RM_OPT_TRIP_LIMIT = 7
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
@@ -26,13 +31,13 @@ EXPORTS = [
     "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
     "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
     "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_set_option", "rm_get_stats",
-    "rm_reset_stats",
+    "rm_reset_stats", "rm_debug_read",
 ]
 
 
 class RmStats(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("taps", C.c_uint64), ("outer_iters", C.c_uint64),
-                ("pixel_samples", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("pixel_samples", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_launches", C.c_uint64),
                 ("render_ms", C.c_double), ("tonemap_ms", C.c_double),
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
@@ -87,5 +92,6 @@ def load() -> C.CDLL:
     lib.rm_set_option.argtypes = [vp, ip, C.c_int64]
     lib.rm_get_stats.argtypes = [vp, C.POINTER(RmStats)]
     lib.rm_reset_stats.argtypes = [vp]
+    lib.rm_debug_read.argtypes = [vp, vp]
     _lib = lib
     return lib

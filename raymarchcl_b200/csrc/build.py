@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libraymarch_b200.so")
-SOURCES = ["rm_api.cu", "rm_kernels.cu"]
+SOURCES = ["rm_api.cu", "rm_kernels.cu", "rm_accel.cu", "rm_render_fast.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
@@ -26,7 +26,10 @@ def _newest_source() -> float:
     return t
 
 
-def build(verbose: bool = True, force: bool = False, extra=()) -> str:
+def build(verbose: bool = True, force: bool = False, extra=(), out: str = OUT) -> str:
+    """Compile the library. `extra` nvcc flags and `out` exist for A/B experiments (load the
+    variant by pointing RAYMARCH_B200_LIB at it)."""
+    OUT = out
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -38,5 +41,10 @@ def build(verbose: bool = True, force: bool = False, extra=()) -> str:
 
 
 if __name__ == "__main__":
-    extra = [a for a in sys.argv[1:] if a != "--force"]
-    build(force=True, extra=extra)
+    argv = sys.argv[1:]
+    out = OUT
+    if "-o" in argv:
+        i = argv.index("-o")
+        out = os.path.abspath(argv[i + 1])
+        del argv[i:i + 2]
+    build(force=True, extra=[a for a in argv if a != "--force"], out=out)

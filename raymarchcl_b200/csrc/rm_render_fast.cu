@@ -21,6 +21,8 @@
 //    voxel box (the test then returns exactly 0 whatever the quotients are).
 //
 // Compiled with -fmad=false like the rest of the library (pinned two-rounding evaluation order).
+#include <cooperative_groups.h>
+
 #include "rm_kernels.h"
 #include "rm_scene_plain.cuh"
 
@@ -206,82 +208,77 @@ RM_DEV void bounce_begin(Lane& L, const Grid& G) {
 namespace {
 
 using namespace fast;
+namespace cg = cooperative_groups;
 
 constexpr int kFastBlock = 128;
+constexpr int kMinMarchIters = 4;
 
 struct FastParams {
   const float4* tables;    // passes x 16384 float4
-  const float* times;      // passes
+  float times[RM_MAX_FUSED_PASSES];  // TRenderOpts.time per pass
   float4* colour;          // passes x slots (null when passes == 1: blend straight into accum)
   float4* accum;
   unsigned long long* queue;
   RmCounters* counters;
   int passes;
+  unsigned* watchdog;      // [0] = tripped flag, [1..15] = state of the first lane that tripped
+  unsigned trip_limit;     // trips round the state machine a lane may take before giving up
   int march_quota;         // max march iterations per trip round the state machine
-  int min_marchers;        // leave the march loop when fewer lanes are marching
+  int min_marchers;        // leave the march loop when fewer lanes are marching together
 };
 
+// Every lane runs its own state machine; nothing below depends on the lanes of a warp being
+// converged (no *_sync intrinsic names a fixed mask): the hardware's SIMT reconvergence only
+// decides how many lanes execute a section together, never what they compute.
 template <bool kCount>
 __global__ void __launch_bounds__(kFastBlock)
 k_render_fast(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard sh,
               const __grid_constant__ RmAccel acc, const __grid_constant__ FastParams P) {
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
   const long long total = (long long)P.passes * sh.slots;
   const Grid G{o, acc, (float)o.rx, (float)o.ry, (float)o.rz};
   Scene s(acc.vox, P.tables, o);
-  Lane L;
+  Lane L = {};
   L.state = S_IDLE;
-  long long poolNext = 0, poolEnd = 0;  // warp-uniform
-  bool exhausted = false;
   const float cellf = (float)(1 << acc.cell_shift);
+  unsigned trips = 0;
 
   for (;;) {
-    // ---- 1. refill idle lanes from the warp pool ----
-    unsigned idle = __ballot_sync(0xffffffffu, L.state == S_IDLE);
-    while (idle && !exhausted) {
-      if (poolNext == poolEnd) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(P.queue, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        poolNext = (long long)base;
-        poolEnd = poolNext + 32 < total ? poolNext + 32 : total;
-        if (poolNext >= total) { exhausted = true; poolNext = poolEnd = 0; break; }
-      }
-      const int avail = (int)(poolEnd - poolNext);
-      const int rank = __popc(idle & lt_mask);
-      if (L.state == S_IDLE && rank < avail) {
-        L.item = poolNext + rank;
-        L.state = S_INIT;
-      }
-      const int want = __popc(idle);
-      poolNext += want < avail ? want : avail;
-      idle = __ballot_sync(0xffffffffu, L.state == S_IDLE);
-    }
-    if (exhausted && L.state == S_IDLE) L.state = S_DONE;
-    if (__all_sync(0xffffffffu, L.state == S_DONE)) break;
+    // ---- 1. a lane without work takes the next item; lanes that are idle at the same time
+    //         share one atomic (coalesced group) and get consecutive items, i.e. adjacent pixels
+    if (L.state == S_IDLE) {
+      cg::coalesced_group grp = cg::coalesced_threads();
+      unsigned long long base = 0;
+      if (grp.thread_rank() == 0) base = atomicAdd(P.queue, (unsigned long long)grp.size());
+      base = grp.shfl(base, 0);
+      L.item = (long long)base + grp.thread_rank();
+      if (L.item >= total) break;  // queue exhausted: this lane is finished
 
-    // ---- 2. item set-up (initRenderState + cameraRayLookat, renderer.cl:456-476) ----
-    if (L.state == S_INIT) {
+      // ---- 2. item set-up (initRenderState + cameraRayLookat, renderer.cl:456-476) ----
       const int pass = (int)(L.item / sh.slots);
       const long long slot = L.item - (long long)pass * sh.slots;
       L.id = rm_slot_to_pixel(sh, slot, o.width, o.height);
-      if (L.id < 0) {
-        L.state = S_IDLE;  // padding slot of an edge tile
-      } else {
-        s.time = __ldg(P.times + pass);
-        s.table = P.tables + (size_t)pass * (RM_TABLE_MASK + 1);
-        L.rd0 = plain::setup_pixel(s, L.id, L.st);
-        trace_begin(L, G, T_PRIMARY, L.st.eye, L.rd0, o.maxDist, o.maxIter);
+      if (L.id < 0) continue;  // padding slot of an edge tile
+      s.time = P.times[pass];
+      s.table = P.tables + (size_t)pass * (RM_TABLE_MASK + 1);
+      L.rd0 = plain::setup_pixel(s, L.id, L.st);
+      trace_begin(L, G, T_PRIMARY, L.st.eye, L.rd0, o.maxDist, o.maxIter);
+    }
+
+    // watchdog: a lane that does not finish within trip_limit trips records why and gives up, so
+    // that a logic error can never hang the device (the host turns the flag into an error)
+    if (++trips > P.trip_limit) {
+      if (atomicCAS(P.watchdog, 0u, 1u) == 0u) {
+        P.watchdog[1] = (unsigned)L.state; P.watchdog[2] = (unsigned)L.tkind; P.watchdog[3] = (unsigned)L.consumer;
+        P.watchdog[4] = (unsigned)L.rem; P.watchdog[5] = (unsigned)L.itersLeft; P.watchdog[6] = (unsigned)L.id;
+        P.watchdog[7] = (unsigned)L.item; P.watchdog[8] = (unsigned)L.li; P.watchdog[9] = (unsigned)L.aoI;
+        P.watchdog[10] = (unsigned)L.bi; P.watchdog[14] = blockIdx.x; P.watchdog[15] = threadIdx.x;
       }
+      break;
     }
 
     // ---- 3. shading transitions (rare, divergent) ----
 #pragma unroll 1
-    for (int round = 0; round < 4; ++round) {
-      const bool slow = L.state >= S_SLOW_FIRST && L.state <= S_SLOW_LAST;
-      if (!__any_sync(0xffffffffu, slow)) break;
-      if (!slow) continue;
+    for (int round = 0; round < 4 && L.state >= S_SLOW_FIRST && L.state <= S_SLOW_LAST; ++round) {
       switch (L.state) {
         case S_TRACE_END: {
           // tail of raymarch (renderer.cl:252-256)
@@ -446,19 +443,22 @@ k_render_fast(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard 
     }
 
     // ---- 5. the march (renderer.cl:219-234) ----
-    for (int it = 0; it < P.march_quota; ++it) {
-      const bool m = L.state == S_MARCH;
-      if ((int)__popc(__ballot_sync(0xffffffffu, m)) < P.min_marchers) break;
-      if (!m) continue;
+#pragma unroll 1
+    for (int it = 0; it < P.march_quota && L.state == S_MARCH; ++it) {
+      // leave early when only a few lanes are still marching together (the others of the warp
+      // are waiting to shade / start their next job); a heuristic, never a correctness matter
+      if (it >= kMinMarchIters && (int)__popc(__activemask()) < P.min_marchers) break;
       const int x = f2i_sat(L.p.x * G.rxf), y = f2i_sat(L.p.y * G.ryf), z = f2i_sat(L.p.z * G.rzf);
       if (kCount) s.w.steps++;
-      if (!in_grid(o, x, y, z)) { L.state = S_MARCH_END; continue; }  // voxelLookup < 0 -> break
+      if (!in_grid(o, x, y, z)) { L.state = S_MARCH_END; break; }  // voxelLookup < 0 -> break
       const int cs = acc.cell_shift;
       const int d = __ldg(acc.dist + ((size_t)(z >> cs) * acc.my + (y >> cs)) * acc.mx + (x >> cs));
       if (d != 0) {
-        // this sample and the next n-1 lie in cells known to hold no solid voxel: advance the
-        // recurrence without fetching
-        int n = 1 + f2i_sat(fminf(((float)(d - 1) * cellf - 0.01f) * L.invS, 1e6f));
+        // This sample and the next n-1 lie in cells known to hold no solid voxel: advance the
+        // recurrence without fetching. Displacement bound: n-1 further steps of at most 1/invS
+        // voxels each stay within (d-1) cells; 0.25 voxel of slack covers the rounding drift.
+        const float reach = (float)(d - 1) * cellf - 0.25f;
+        int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * L.invS, 1e6f)) : 1;
         n = n < L.rem ? n : L.rem;
         L.rem -= n;
         if (kCount) {
@@ -478,7 +478,7 @@ k_render_fast(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard 
         if ((w >> brick_bit(x, y, z)) & 1ull) {
           L.hit = true;
           L.state = S_MARCH_END;
-          continue;
+          break;
         }
         L.p = L.p + L.delta;
         L.rem -= 1;
@@ -511,24 +511,18 @@ k_render_fast(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard 
   }
 
   if (kCount) {
-    unsigned long long a = s.w.steps, b = s.w.taps, c = s.w.outer;
-    for (int off = 16; off > 0; off >>= 1) {
-      a += __shfl_down_sync(0xffffffffu, a, off);
-      b += __shfl_down_sync(0xffffffffu, b, off);
-      c += __shfl_down_sync(0xffffffffu, c, off);
-    }
-    if (lane == 0) {
-      atomicAdd(&P.counters->steps, a);
-      atomicAdd(&P.counters->taps, b);
-      atomicAdd(&P.counters->outer, c);
-    }
+    atomicAdd(&P.counters->steps, (unsigned long long)s.w.steps);
+    atomicAdd(&P.counters->taps, (unsigned long long)s.w.taps);
+    atomicAdd(&P.counters->outer, (unsigned long long)s.w.outer);
   }
 }
+
+struct BlendWeights { float w[RM_MAX_FUSED_PASSES]; };
 
 // Blend the per-pass colours of one launch into the accumulator in pass order:
 // pixels = mix(pixels, colour, frameBlend) per pass (renderer.cl:492).
 __global__ void __launch_bounds__(256)
-k_blend_passes(const float4* __restrict__ colour, const float* __restrict__ blend, int passes,
+k_blend_passes(const float4* __restrict__ colour, const __grid_constant__ BlendWeights bw, int passes,
                const __grid_constant__ RmShard sh, int W, int H, float4* __restrict__ accum) {
   const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
   if (slot >= sh.slots) return;
@@ -538,7 +532,7 @@ k_blend_passes(const float4* __restrict__ colour, const float* __restrict__ blen
   float3 p = f3(old.x, old.y, old.z);
   for (int k = 0; k < passes; ++k) {
     const float4 c = __ldcs(colour + (size_t)k * sh.slots + slot);
-    p = lerp3(p, f3(c.x, c.y, c.z), __ldg(blend + k));
+    p = lerp3(p, f3(c.x, c.y, c.z), bw.w[k]);
   }
   accum[id] = make_float4(p.x, p.y, p.z, 1.0f);
 }
@@ -553,17 +547,26 @@ int rm_fast_blocks_per_sm(int count) {
 }
 
 cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
-                                  const float4* d_tables, const float* d_times, const float* d_blend,
+                                  const float4* d_tables, const float* times, const float* blend,
                                   int passes, float4* d_colour, float4* d_accum,
                                   unsigned long long* d_queue, RmCounters* d_counters, int grid_blocks,
-                                  int march_quota, int min_marchers, cudaStream_t stream) {
+                                  int march_quota, int min_marchers, unsigned* d_watchdog, unsigned trip_limit,
+                                  cudaStream_t stream) {
   if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
+  if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
   FastParams P;
-  P.tables = d_tables; P.times = d_times; P.colour = passes > 1 ? d_colour : nullptr; P.accum = d_accum;
+  P.tables = d_tables;
+  BlendWeights bw;
+  for (int i = 0; i < RM_MAX_FUSED_PASSES; ++i) {
+    P.times[i] = i < passes ? times[i] : 0.0f;
+    bw.w[i] = i < passes ? blend[i] : 0.0f;
+  }
+  P.colour = passes > 1 ? d_colour : nullptr; P.accum = d_accum;
   P.queue = d_queue; P.counters = d_counters; P.passes = passes;
   P.march_quota = march_quota; P.min_marchers = min_marchers;
+  P.watchdog = d_watchdog; P.trip_limit = trip_limit;
   const long long total = (long long)passes * shard.slots;
   long long need = (total + kFastBlock - 1) / kFastBlock;
   const unsigned blocks = (unsigned)(need < grid_blocks ? need : grid_blocks);
@@ -573,7 +576,7 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
     k_render_fast<false><<<blocks, kFastBlock, 0, stream>>>(opts, shard, accel, P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (passes > 1) {
-    k_blend_passes<<<(unsigned)((shard.slots + 255) / 256), 256, 0, stream>>>(d_colour, d_blend, passes, shard,
+    k_blend_passes<<<(unsigned)((shard.slots + 255) / 256), 256, 0, stream>>>(d_colour, bw, passes, shard,
                                                                             opts.width, opts.height, d_accum);
     e = cudaGetLastError();
   }

@@ -184,3 +184,45 @@ def test_full_size_property_idempotent_and_deterministic(gpu_renderer):
         acc += gpu_renderer.read_accum().astype(np.float64).sum(axis=(1, 2))
     gpu_renderer.set_tile_shard(0, 1, 32, 32)
     assert np.array_equal(acc, rowsum)
+
+
+@pytest.mark.parametrize("knobs", [
+    {3: 2}, {3: 3}, {3: 4}, {4: 1, 5: 1}, {4: 4, 5: 32}, {4: 1000, 5: 1}, {6: 1}, {6: 2},
+], ids=lambda k: "-".join(f"{a}={b}" for a, b in k.items()))
+def test_fast_kernel_tuning_knobs_do_not_change_results(gpu_renderer, knobs):
+    """Macro-cell size, march quota / leave threshold and the pass-fusion limit are scheduling
+    choices only: accumulator bits and work counters must not move."""
+    kw = dict(vres=96, width=120, height=72, iters=3, mat="metal")
+    vol, opts, mcs = build_scene(**kw)
+    gpu_renderer.set_option(2, 1)
+    ref, _, cref = render_gpu(gpu_renderer, vol, opts, mcs, 120, 72)
+    gpu_renderer.set_option(2, 0)
+    try:
+        for k, v in knobs.items():
+            gpu_renderer.set_option(k, v)
+        px, _, cnt = render_gpu(gpu_renderer, vol, opts, mcs, 120, 72)
+        px_nc, _, _ = render_gpu(gpu_renderer, vol, opts, mcs, 120, 72, count=False)
+    finally:
+        for k, v in {3: 0, 4: 32, 5: 12, 6: 32}.items():
+            gpu_renderer.set_option(k, v)
+    assert np.array_equal(cnt, cref)
+    assert np.array_equal(px.view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(px_nc.view(np.uint32), ref.view(np.uint32))
+
+
+def test_fast_kernel_iso_boundary_and_non_uniform_passes(gpu_renderer, oracle):
+    """Voxels exactly at isoVal are NOT solid for the march (v > iso) but DO count as occupied for
+    normals (v >= iso); passes whose opts differ in more than `time` cannot share a launch."""
+    kw = dict(vres=64, width=96, height=64, iters=3, mat="metal")
+    vol, opts, mcs = build_scene(**kw)
+    vol = vol.copy()
+    vol[vol == 64] = 32  # one band sits exactly on the iso value
+    from raymarchcl_b200.options import decode_render_opts, encode_render_opts
+    f = decode_render_opts(opts[1])
+    f["eyePos"] = [1.2, 0.5, -1.9]
+    opts = [opts[0], encode_render_opts(f), opts[2]]
+    ref_px, ref_cnt = oracle.render_frame(vol, mcs, opts, 96, 64)
+    gpu_renderer.set_option(2, 0)
+    px, argb, cnt = render_gpu(gpu_renderer, vol, opts, mcs, 96, 64)
+    assert np.array_equal(cnt, ref_cnt)
+    check_frame(px, ref_px, argb, oracle.tonemap(ref_px, opts[0]))
