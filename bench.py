@@ -41,6 +41,9 @@ WORKLOADS = {
     # BASELINE.json configs[1] -- the configuration the metric is quoted on
     "c2": dict(name="256^3 gyroid, 1920x1080, 16 passes, :metal, dof 0.001 (BASELINE configs[1])",
                scene=dict(vres=256, width=1920, height=1080, iters=16, mat="metal")),
+    # reduced copy of c2 for profiling under ncu (kernel replays): quarter frame, 4 passes
+    "c2s": dict(name="256^3 gyroid, 960x540, 4 passes, :metal (reduced c2, profiling only)",
+                scene=dict(vres=256, width=960, height=540, iters=4, mat="metal")),
     # the other configs are parity-test cases; selectable here for exploration only
     "c1": dict(name="64^3 gyroid, 256x256, 1 pass, :ao (BASELINE configs[0])",
                scene=dict(vres=64, width=256, height=256, iters=1, mat="ao")),

@@ -72,11 +72,7 @@ typedef enum rm_option {
   RM_OPT_KERNEL = 2,       /* 0 = default fast kernel; 1 = plain one-thread-per-pixel kernel */
   /* tuning knobs of the fast kernel; none of them changes results */
   RM_OPT_CELL_SHIFT = 3,   /* macro-cell edge of the distance map = 1<<value voxels; 0 = auto (~res/64) */
-  RM_OPT_MARCH_QUOTA = 4,  /* march iterations per trip round the lane state machine */
-  RM_OPT_MIN_MARCHERS = 5, /* leave the march loop when fewer lanes of the warp are marching */
-  RM_OPT_FUSE_LIMIT = 6,   /* max passes rendered by one launch (1..32) */
-  RM_OPT_TRIP_LIMIT = 7    /* watchdog: state-machine trips a warp may take per launch before the
-                              launch is abandoned with RM_ERR_CUDA (default 2^28) */
+  RM_OPT_FUSE_LIMIT = 6    /* max passes rendered by one launch (1..32) */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */
@@ -131,8 +127,7 @@ int64_t rm_shard_pixels(const rm_ctx* ctx);
 int rm_set_option(rm_ctx* ctx, int option, int64_t value);
 int rm_get_stats(const rm_ctx* ctx, rm_stats* out);
 int rm_reset_stats(rm_ctx* ctx);
-/* Diagnostic: the 32 watchdog / debug words of the render kernel (see RM_OPT_TRIP_LIMIT). */
-int rm_debug_read(rm_ctx* ctx, uint32_t* out32);
+
 
 #ifdef __cplusplus
 }

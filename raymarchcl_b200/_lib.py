@@ -20,10 +20,7 @@ STATUS_NAMES = {0: "RM_OK", -1: "RM_ERR_INVALID_ARG", -2: "RM_ERR_BAD_OPTS", -3:
 RM_OPT_COUNT_WORK = 1
 RM_OPT_KERNEL = 2
 RM_OPT_CELL_SHIFT = 3
-RM_OPT_MARCH_QUOTA = 4
-RM_OPT_MIN_MARCHERS = 5
 RM_OPT_FUSE_LIMIT = 6
-RM_OPT_TRIP_LIMIT = 7
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
@@ -31,7 +28,7 @@ EXPORTS = [
     "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
     "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
     "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_set_option", "rm_get_stats",
-    "rm_reset_stats", "rm_debug_read",
+    "rm_reset_stats",
 ]
 
 
@@ -92,6 +89,5 @@ def load() -> C.CDLL:
     lib.rm_set_option.argtypes = [vp, ip, C.c_int64]
     lib.rm_get_stats.argtypes = [vp, C.POINTER(RmStats)]
     lib.rm_reset_stats.argtypes = [vp]
-    lib.rm_debug_read.argtypes = [vp, vp]
     _lib = lib
     return lib

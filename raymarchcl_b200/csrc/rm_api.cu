@@ -59,13 +59,9 @@ struct rm_ctx {
   RmAccelStorage accel;
   float4* d_colour = nullptr;       // per-pass colours of one fused launch
   size_t colour_capacity = 0;       // float4 elements
-  unsigned long long* d_queue = nullptr;
-  unsigned* d_watchdog = nullptr;   // 16 words, see rm_launch_render_fast
-  unsigned trip_limit = 1u << 28;
   int num_sms = 0;
-  int fast_blocks[2] = {0, 0};      // resident blocks per SM: [0] plain variant, [1] counting variant
   int cell_shift_opt = 0;           // 0 = auto
-  int march_quota = 32, min_marchers = 12, fuse_limit = RM_MAX_FUSED_PASSES;
+  int fuse_limit = RM_MAX_FUSED_PASSES;
 
   rm_stats stats{};
   std::vector<EventPair> pending, free_events;
@@ -253,14 +249,9 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
       }
       float times[RM_MAX_FUSED_PASSES], blend[RM_MAX_FUSED_PASSES];
       for (int k = 0; k < m; ++k) { times[k] = passes[i + k].time; blend[k] = passes[i + k].frameBlend; }
-      const int variant = cnt ? 1 : 0;
-      if (!c->fast_blocks[variant]) c->fast_blocks[variant] = rm_fast_blocks_per_sm(variant);
-      if (c->fast_blocks[variant] <= 0) return fail(c, RM_ERR_CUDA, "render kernel does not fit on an SM");
       EventPair t = begin_timed(c, 0);
       cudaError_t e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
-                                            c->d_colour, c->d_accum, c->d_queue, cnt,
-                                            c->fast_blocks[variant] * c->num_sms, c->march_quota, c->min_marchers,
-                                            c->d_watchdog, c->trip_limit, c->stream);
+                                            c->d_colour, c->d_accum, cnt, c->stream);
       end_timed(c, t);
       if (e != cudaSuccess) return cuda_fail(c, e, "render kernel launch");
       c->stats.kernel_launches += m > 1 ? 2 : 1;
@@ -271,22 +262,6 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
   c->stats.pixel_samples += (uint64_t)rm_shard_pixels(c) * (uint64_t)n;
   if (c->pending.size() > 512) resolve_timers(c);
   return RM_OK;
-}
-
-// After a synchronisation point: did a render warp give up (rm_launch_render_fast watchdog)?
-int check_watchdog(rm_ctx* c) {
-  if (c->kernel_kind == 1) return RM_OK;
-  unsigned w[16];
-  RM_CUDA(c, cudaMemcpy(w, c->d_watchdog, sizeof w, cudaMemcpyDeviceToHost));
-  if (!w[0]) return RM_OK;
-  cudaMemset(c->d_watchdog, 0, sizeof w);
-  char msg[320];
-  std::snprintf(msg, sizeof msg,
-                "render kernel watchdog: a warp exceeded %u trips (lane state %u trace %u consumer %u rem %d iters %d "
-                "pixel %u item %u light %u ao %u bounce %u exhausted %u pool %u..%u block %u thread %u)",
-                c->trip_limit, w[1], w[2], w[3], (int)w[4], (int)w[5], w[6], w[7], w[8], w[9], w[10], w[11], w[12], w[13],
-                w[14], w[15]);
-  return fail(c, RM_ERR_CUDA, msg);
 }
 
 int require_ready(rm_ctx* c) {
@@ -333,9 +308,6 @@ int rm_create(int device_id, rm_ctx** out_ctx) {
   if ((e = cudaSetDevice(device_id)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMalloc(&c->d_counters, sizeof(RmCounters))) != cudaSuccess ||
-      (e = cudaMalloc(&c->d_queue, sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMalloc(&c->d_watchdog, 32 * sizeof(unsigned))) != cudaSuccess ||
-      (e = cudaMemset(c->d_watchdog, 0, 32 * sizeof(unsigned))) != cudaSuccess ||
       (e = cudaMemset(c->d_counters, 0, sizeof(RmCounters))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "rm_create");
     delete c;
@@ -355,7 +327,7 @@ void rm_destroy(rm_ctx* c) {
   resolve_timers(c);
   for (EventPair& p : c->free_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_tables); cudaFree(c->d_counters);
-  cudaFree(c->d_colour); cudaFree(c->d_queue); cudaFree(c->d_watchdog);
+  cudaFree(c->d_colour);
   rm_accel_free(&c->accel);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -438,7 +410,7 @@ int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, 
   c->stats.h2d_bytes += tbytes * iter + (size_t)RM_OPTS_BYTES * iter;
   if ((rc = launch_passes(c, dec.data(), iter, c->d_tables))) return rc;
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  return check_watchdog(c);
+  return RM_OK;
 }
 
 int rm_upload_passes(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
@@ -499,7 +471,6 @@ int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out)
   end_timed(c, t2);
   if (e != cudaSuccess) return cuda_fail(c, e, "argb read-back");
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  if ((rc = check_watchdog(c))) return rc;
   std::memcpy(argb_out, c->h_stage, n * sizeof(uint32_t));
   c->stats.d2h_bytes += n * sizeof(uint32_t);
   return RM_OK;
@@ -545,14 +516,14 @@ int rm_read_accum(rm_ctx* c, float* rgba_out) {
   RM_CUDA(c, cudaMemcpyAsync(rgba_out, c->d_accum, bytes, cudaMemcpyDeviceToHost, c->stream));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stats.d2h_bytes += bytes;
-  return check_watchdog(c);
+  return RM_OK;
 }
 
 int rm_sync(rm_ctx* c) {
   if (!c) return RM_ERR_INVALID_ARG;
   RM_CUDA(c, cudaSetDevice(c->device));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  return check_watchdog(c);
+  return RM_OK;
 }
 
 int rm_set_stream(rm_ctx* c, void* cuda_stream) {
@@ -587,13 +558,6 @@ int64_t rm_shard_pixels(const rm_ctx* c) {
   return px;
 }
 
-int rm_debug_read(rm_ctx* c, uint32_t* out32) {
-  if (!c || !out32) return RM_ERR_INVALID_ARG;
-  RM_CUDA(c, cudaSetDevice(c->device));
-  RM_CUDA(c, cudaMemcpy(out32, c->d_watchdog, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost));
-  return RM_OK;
-}
-
 int rm_set_option(rm_ctx* c, int option, int64_t value) {
   if (!c) return RM_ERR_INVALID_ARG;
   switch (option) {
@@ -606,18 +570,6 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
       if (value < 0 || value > 6 || value == 1) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_CELL_SHIFT: 0 (auto) or 2..6");
       c->cell_shift_opt = (int)value;
       c->accel.valid = false;
-      return RM_OK;
-    case RM_OPT_MARCH_QUOTA:
-      if (value < 1 || value > 4096) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_MARCH_QUOTA: 1..4096");
-      c->march_quota = (int)value;
-      return RM_OK;
-    case RM_OPT_MIN_MARCHERS:
-      if (value < 1 || value > 32) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_MIN_MARCHERS: 1..32");
-      c->min_marchers = (int)value;
-      return RM_OK;
-    case RM_OPT_TRIP_LIMIT:
-      if (value < 1 || value > 0xffffffffLL) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_TRIP_LIMIT: 1..2^32-1");
-      c->trip_limit = (unsigned)value;
       return RM_OK;
     case RM_OPT_FUSE_LIMIT:
       if (value < 1 || value > RM_MAX_FUSED_PASSES) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_FUSE_LIMIT: 1..32");

@@ -19,7 +19,8 @@ k_render_plain(const uint8_t* __restrict__ vox, const float4* __restrict__ table
   if (slot < sh.slots) {
     const int id = rm_slot_to_pixel(sh, slot, o.width, o.height);
     if (id >= 0) {
-      const float3 c = plain::render_pixel_sample(s, id);
+      const plain::ByteVolume V{vox};
+      const float3 c = plain::render_pixel_sample<kCount>(s, V, id);
       const float4 old = accum[id];
       const float3 m = lerp3(f3(old.x, old.y, old.z), c, o.frameBlend);  // mix(), renderer.cl:492
       accum[id] = make_float4(m.x, m.y, m.z, 1.0f);

@@ -42,18 +42,11 @@ cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso
                            RmAccelStorage* st, cudaStream_t stream);
 void rm_accel_free(RmAccelStorage* st);
 
-// Resident blocks per SM of the persistent render kernel (count != 0: the counting variant).
-int rm_fast_blocks_per_sm(int count);
-
 // RenderImage-equivalent for `passes` (<= RM_MAX_FUSED_PASSES) consecutive passes whose opts differ
-// only in `time` / `frameBlend`: one persistent launch over (pixel, pass) items + one blend launch
+// only in `time` / `frameBlend`: one launch over (pixel, pass) items + one blend launch
 // (passes == 1: the render kernel blends into d_accum itself). d_tables = the passes' tables,
 // contiguous; times / blend = per-pass TRenderOpts.time / frameBlend (host arrays, passed by value).
 cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                   const float4* d_tables, const float* times, const float* blend,
-                                  int passes, float4* d_colour, float4* d_accum,
-                                  unsigned long long* d_queue, RmCounters* d_counters, int grid_blocks,
-                                  int march_quota, int min_marchers, unsigned* d_watchdog, unsigned trip_limit,
+                                  int passes, float4* d_colour, float4* d_accum, RmCounters* d_counters,
                                   cudaStream_t stream);
-// d_watchdog: 16 words, zeroed by the caller; word 0 != 0 after the launch means a warp exceeded
-// trip_limit trips round its state machine and gave up (the frame is then incomplete).

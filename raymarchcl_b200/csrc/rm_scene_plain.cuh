@@ -1,7 +1,19 @@
-// rm_scene_plain.cuh -- the render op as one self-contained per-pixel routine over the raw uint8
-// volume: the straightforward CUDA form of RenderImage (renderer.cl:478-494 and its call tree).
-// It is the in-library comparison kernel (RM_OPT_KERNEL = 1): same results as the fast kernel,
-// no acceleration data, one thread per pixel-sample.
+// rm_scene_plain.cuh -- the render op as one per-pixel-sample routine: the CUDA form of
+// RenderImage (renderer.cl:478-494 and its call tree), templated on how the volume is read:
+//
+//   ByteVolume   the raw uint8 grid, one byte per reference fetch. This is the in-library
+//                comparison kernel (RM_OPT_KERNEL = 1): no derived data at all.
+//   BrickVolume  the occupancy data of rm_accel.cu: the march predicate comes from 4x4x4
+//                bit-bricks, and a macro-cell Chebyshev distance map says how many of the next
+//                samples of the fixed-step march cannot be solid, so that those samples cost
+//                three adds (the fp32 recurrence p += delta is part of the result) and no fetch.
+//
+// Both evaluate the surface normal once per sphere-trace, from the hit of the LAST
+// distanceToScene call (the reference recomputes it at every outer iteration and overwrites it,
+// renderer.cl:224-228, so only the last one is ever visible), and both skip the slab test's six
+// IEEE divisions when the ray origin is strictly inside the voxel box (the test then returns
+// exactly +0 whatever the quotients are). Results are identical to the reference's order of
+// operations; the oracle checks that bit for bit on the work counters.
 #pragma once
 #include "rm_math.cuh"
 #include "rm_types.h"
@@ -53,78 +65,222 @@ RM_DEV bool in_grid(const RmOpts& o, int x, int y, int z) {
   return (unsigned)x < (unsigned)o.rx && (unsigned)y < (unsigned)o.ry && (unsigned)z < (unsigned)o.rz;
 }
 
-// renderer.cl:172-178
-RM_DEV float occupancy(Scene& s, int x, int y, int z) {
-  s.w.taps++;
-  if (!in_grid(s.o, x, y, z)) return 0.0f;
-  const int v = __ldg(s.vox + ((size_t)z * s.o.rxy + (size_t)y * s.o.rx + x));
-  return v < s.o.isoVal ? 0.0f : 1.0f;
+// ---- volume access policies ----------------------------------------------------------------
+
+struct ByteVolume {
+  const uint8_t* __restrict__ vox;
+  RM_DEV int value(const RmOpts& o, int x, int y, int z) const {
+    return __ldg(vox + ((size_t)z * o.rxy + (size_t)y * o.rx + x));
+  }
+  // voxelLookupI (renderer.cl:172-178): v >= isoVal, 0 outside the grid
+  RM_DEV int occ(const RmOpts& o, int x, int y, int z) const {
+    if (!in_grid(o, x, y, z)) return 0;
+    return value(o, x, y, z) >= o.isoVal ? 1 : 0;
+  }
+};
+
+struct BrickVolume {
+  const RmAccel& a;
+  float cellf;
+  RM_DEV uint64_t word(const uint64_t* __restrict__ bricks, int x, int y, int z) const {
+    return __ldg(bricks + ((size_t)(z >> 2) * a.by + (y >> 2)) * a.bx + (x >> 2));
+  }
+  static RM_DEV unsigned bit(int x, int y, int z) { return (x & 3) | ((y & 3) << 2) | ((z & 3) << 4); }
+  RM_DEV int value(const RmOpts& o, int x, int y, int z) const {
+    return __ldg(a.vox + ((size_t)z * o.rxy + (size_t)y * o.rx + x));
+  }
+  RM_DEV int occ(const RmOpts& o, int x, int y, int z) const {
+    if (!in_grid(o, x, y, z)) return 0;
+    return (int)((word(a.occ, x, y, z) >> bit(x, y, z)) & 1ull);
+  }
+};
+
+// voxelNormal (renderer.cl:180-188) as integers: -(occ(+1) - occ(-1)) per axis
+template <class Vol>
+RM_DEV void gradient6_i(const Vol& V, const RmOpts& o, int x, int y, int z, int& gx, int& gy, int& gz) {
+  gx = V.occ(o, x - 1, y, z) - V.occ(o, x + 1, y, z);
+  gy = V.occ(o, x, y - 1, z) - V.occ(o, x, y + 1, z);
+  gz = V.occ(o, x, y, z - 1) - V.occ(o, x, y, z + 1);
 }
 
-// renderer.cl:180-188
-RM_DEV float3 gradient6(Scene& s, int x, int y, int z) {
-  const float gx = occupancy(s, x + 1, y, z) - occupancy(s, x - 1, y, z);
-  const float gy = occupancy(s, x, y + 1, z) - occupancy(s, x, y - 1, z);
-  const float gz = occupancy(s, x, y, z + 1) - occupancy(s, x, y, z - 1);
-  return f3(-gx, -gy, -gz);
+// unit3(voxelNormal): the reference negates a float difference, so equal taps give -0.0f
+template <class Vol>
+RM_DEV float3 normal_6tap(const Vol& V, const RmOpts& o, int x, int y, int z) {
+  int gx, gy, gz;
+  gradient6_i(V, o, x, y, z, gx, gy, gz);
+  return unit3(f3(-(float)(-gx), -(float)(-gy), -(float)(-gz)));
 }
 
-// renderer.cl:190-203
-RM_DEV float3 gradient27(Scene& s, int x, int y, int z) {
-  float3 n = f3s(0.0f);
+// voxelNormalSmooth (renderer.cl:190-203): the reference's float sums are sums of small
+// integers, hence exact (and never -0): the integer sum converted once is the same value.
+template <class Vol>
+RM_DEV float3 normal_smooth(const Vol& V, const RmOpts& o, int x, int y, int z) {
+  int sx = 0, sy = 0, sz = 0;
   for (int dz = -1; dz <= 1; ++dz)
     for (int dy = -1; dy <= 1; ++dy)
       for (int dx = -1; dx <= 1; ++dx)
-        if (occupancy(s, x + dx, y + dy, z + dz) > 0.0f) n = n + gradient6(s, x + dx, y + dy, z + dz);
-  return unit3(n);
+        if (V.occ(o, x + dx, y + dy, z + dz)) {
+          int gx, gy, gz;
+          gradient6_i(V, o, x + dx, y + dy, z + dz, gx, gy, gz);
+          sx += gx; sy += gy; sz += gz;
+        }
+  return unit3(f3((float)sx, (float)sy, (float)sz));
 }
 
-// renderer.cl:209-237. Returns (distance, id); writes *normal where the reference writes isec->normal.
-RM_DEV float2 scene_distance(Scene& s, float3 rpos, float3 dir, int steps, bool smooth, float3* normal) {
+// reference-equivalent occupancy taps of one hit (counting mode only)
+template <class Vol>
+RM_DEV unsigned taps_of_hit(const Vol& V, const RmOpts& o, int x, int y, int z, bool smooth) {
+  if (!smooth) return 6u;
+  unsigned n = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) n += V.occ(o, x + dx, y + dy, z + dz);
+  return 27u + 6u * n;
+}
+
+// One distanceToScene call (renderer.cl:209-237) without its normal: what the march found.
+struct JobResult {
+  float dist;     // .x of the returned pair
+  float g;        // ground-plane distance of this call (the ground's "id" is (int)g, :211)
+  bool hit;       // the march stopped on a solid voxel at sample position p
+  bool closer;    // ... and the voxel distance won against the ground plane
+  float3 p;
+};
+
+// The fixed-step march (renderer.cl:219-234). Returns true on a solid voxel; p is then the
+// sample position of the hit.
+template <bool kCount>
+RM_DEV bool march(Scene& s, const ByteVolume& V, float3& p, float3 delta, int steps, float) {
   const RmOpts& o = s.o;
-  const float g = rpos.y + o.groundY;
-  float2 res = (g < 1e5f) ? make_float2(g, g) : make_float2(1e5f, -1.0f);
-  *normal = (res.x < 1e5f) ? f3(0.0f, 1.0f, 0.0f) : -dir;
-  const float idist = box_entry(o.boundsMin, o.boundsMax, rpos, dir);
-  if (idist >= 0.0f && idist < res.x) {
-    const float3 delta = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
+  while (--steps >= 0) {
+    const int x = f2i_sat(p.x * (float)o.rx), y = f2i_sat(p.y * (float)o.ry), z = f2i_sat(p.z * (float)o.rz);
+    if (kCount) s.w.steps++;
+    if (!in_grid(o, x, y, z)) return false;  // voxelLookup < 0 -> break
+    if (V.value(o, x, y, z) > o.isoVal) return true;
+    p = p + delta;
+  }
+  return false;
+}
+
+template <bool kCount>
+RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
+  const RmOpts& o = s.o;
+  const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
+  const int cs = V.a.cell_shift;
+  while (rem > 0) {
+    const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
+    if (kCount) s.w.steps++;
+    if (!in_grid(o, x, y, z)) return false;
+    const int d = __ldg(V.a.dist + ((size_t)(z >> cs) * V.a.my + (y >> cs)) * V.a.mx + (x >> cs));
+    if (d != 0) {
+      // This sample and the next n-1 lie in cells known to hold no solid voxel: advance the
+      // recurrence without fetching. n-1 further steps of at most 1/invS voxels each stay within
+      // (d-1) cells; 0.25 voxel of slack covers the rounding drift of the recurrence.
+      const float reach = (float)(d - 1) * V.cellf - 0.25f;
+      int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
+      n = n < rem ? n : rem;
+      rem -= n;
+      if (kCount) {
+        for (int j = 1; j <= n; ++j) {
+          p = p + delta;
+          if (j < n) {  // the reference fetches (and counts) every one of these samples
+            s.w.steps++;
+            if (!in_grid(o, f2i_sat(p.x * rxf), f2i_sat(p.y * ryf), f2i_sat(p.z * rzf))) return false;
+          }
+        }
+      } else {
+        for (int j = 0; j < n; ++j) p = p + delta;
+      }
+    } else {
+      if ((V.word(V.a.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
+      p = p + delta;
+      rem -= 1;
+    }
+  }
+  return false;
+}
+
+// renderer.cl:209-237 without the normal
+template <bool kCount, class Vol>
+RM_DEV JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float3 dir, float3 delta, int steps, float invS,
+                                bool smooth) {
+  const RmOpts& o = s.o;
+  JobResult r;
+  r.g = rpos.y + o.groundY;
+  r.dist = r.g < 1e5f ? r.g : 1e5f;
+  r.hit = false;
+  r.closer = false;
+  r.p = f3s(0.0f);
+  const bool inside = rpos.x > o.boundsMin.x && rpos.x < o.boundsMax.x && rpos.y > o.boundsMin.y &&
+                      rpos.y < o.boundsMax.y && rpos.z > o.boundsMin.z && rpos.z < o.boundsMax.z;
+  // strictly inside: every entry quotient is < 0 and every exit quotient > 0, so the slab test
+  // returns max(..., 0) = +0 without evaluating the divisions
+  const float idist = inside ? 0.0f : box_entry(o.boundsMin, o.boundsMax, rpos, dir);
+  if (idist >= 0.0f && idist < r.dist) {
     float3 p = rpos + o.voxelBounds;
     if (idist > 0.0f) p = dir * idist + p;
     p = p * o.invVoxelScale;
-    while (--steps >= 0) {
-      const int x = f2i_sat(p.x * (float)o.rx), y = f2i_sat(p.y * (float)o.ry), z = f2i_sat(p.z * (float)o.rz);
-      s.w.steps++;
-      if (!in_grid(o, x, y, z)) break;
-      const int v = __ldg(s.vox + ((size_t)z * o.rxy + (size_t)y * o.rx + x));
-      if (v > o.isoVal) {
-        *normal = smooth ? gradient27(s, x, y, z) : unit3(gradient6(s, x, y, z));
-        const float3 hp = p * o.voxelBounds2 + (-o.voxelBounds);
-        const float d = len3(rpos - hp) - o.voxelSize;
-        const float band = v < 168 ? (v < 84 ? 1.0f : 2.0f) : 3.0f;  // renderer.cl:205-207
-        return d < res.x ? make_float2(d, band) : res;
+    if (march<kCount>(s, V, p, delta, steps, invS)) {
+      r.hit = true;
+      r.p = p;
+      if (kCount) {
+        const int x = f2i_sat(p.x * (float)o.rx), y = f2i_sat(p.y * (float)o.ry), z = f2i_sat(p.z * (float)o.rz);
+        s.w.taps += taps_of_hit(V, o, x, y, z, smooth);
       }
-      p = p + delta;
+      const float3 hp = p * o.voxelBounds2 + (-o.voxelBounds);
+      const float d = len3(rpos - hp) - o.voxelSize;
+      if (d < r.dist) { r.dist = d; r.closer = true; }
     }
   }
-  return res;
+  return r;
+}
+
+// per-direction constants of the march: delta (renderer.cl:215) and 1 / (largest step in voxels)
+RM_DEV float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
+  const float3 delta = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
+  const float sm = fmaxf(fmaxf(fabsf(delta.x) * (float)o.rx, fabsf(delta.y) * (float)o.ry), fabsf(delta.z) * (float)o.rz);
+  invS = sm > 1e-12f ? __fdividef(1.0f, sm) : 1e12f;
+  return delta;
 }
 
 // renderer.cl:239-257
-RM_DEV void sphere_trace(Scene& s, float3 ro, float3 rd, Isec& r, float maxDist, int maxSteps, bool smooth) {
-  r.distance = s.o.startDist;
+template <bool kCount, class Vol>
+RM_DEV void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Isec& r, float maxDist, int maxSteps,
+                         bool smooth, bool wantSurface) {
+  const RmOpts& o = s.o;
+  float invS;
+  const float3 delta = march_delta(o, rd, o.maxVoxelIter, invS);
+  JobResult j;
+  j.g = 0.0f; j.dist = 0.0f; j.hit = false; j.closer = false; j.p = f3s(0.0f);
+  r.distance = o.startDist;
+  r.pos = ro;
   while (--maxSteps >= 0) {
-    s.w.outer++;
+    if (kCount) s.w.outer++;
     r.pos = ro + rd * r.distance;
-    const float2 h = scene_distance(s, r.pos, rd, s.o.maxVoxelIter, smooth, &r.normal);
-    r.objectID = f2i_sat(h.y);
-    if (fabsf(h.x) <= s.o.eps || r.distance >= maxDist) break;
-    r.distance += h.x;
+    j = scene_distance<kCount>(s, V, r.pos, rd, delta, o.maxVoxelIter, invS, smooth);
+    if (fabsf(j.dist) <= o.eps || r.distance >= maxDist) break;
+    r.distance += j.dist;
   }
-  if (r.distance >= maxDist) {
+  const bool miss = r.distance >= maxDist;
+  if (miss) {
     r.pos = ro + rd * r.distance;
-    r.objectID = -1;
     r.distance = 1000.0f;
   }
+  r.objectID = -1;
+  r.normal = f3s(0.0f);
+  if (!wantSurface) return;  // shadow rays use the distance only
+  // object id and normal of the LAST distanceToScene call
+  const int x = f2i_sat(j.p.x * (float)o.rx), y = f2i_sat(j.p.y * (float)o.ry), z = f2i_sat(j.p.z * (float)o.rz);
+  if (!miss) {
+    if (j.closer) {
+      const int v = V.value(o, x, y, z);
+      r.objectID = v < 168 ? (v < 84 ? 1 : 2) : 3;  // voxelMaterial, renderer.cl:205-207
+    } else {
+      r.objectID = f2i_sat(j.g < 1e5f ? j.g : -1.0f);
+    }
+  }
+  if (j.hit) r.normal = smooth ? normal_smooth(V, o, x, y, z) : normal_6tap(V, o, x, y, z);
+  else r.normal = j.g < 1e5f ? f3(0.0f, 1.0f, 0.0f) : -rd;
 }
 
 RM_DEV float3 sky(const RmOpts& o, float3 d) { return lerp3(o.sky1, o.sky2, d.y * 0.5f + 0.5f); }  // :259-261
@@ -172,7 +328,8 @@ RM_DEV float blinn_phong(float smooth, float3 rd, float3 ldir, float3 n) {
 }
 
 // renderer.cl:327-346
-RM_DEV float ambient_occlusion(Scene& s, float3 pos, float3 n0) {
+template <bool kCount, class Vol>
+RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
   const RmOpts& o = s.o;
   float ao = 1.0f, d = 0.0f;
   uint32_t seed = f2u_wrap(pos.x * 3183.75f + pos.y * 1831.42f + pos.z * 2945.87f + s.time * 2671.918f);
@@ -180,18 +337,20 @@ RM_DEV float ambient_occlusion(Scene& s, float3 pos, float3 n0) {
     d += o.aoStepDist;
     seed += 37u;
     const float3 n = unit3(table_xyz(s, seed) * 0.2f + n0);
-    float3 unused;
-    const float2 h = scene_distance(s, n * d + pos, n, o.maxVoxelIter / 2, false, &unused);
-    ao *= 1.0f - cl_max((d - h.x) * o.aoAmp / d, 0.0f);
+    float invS;
+    const float3 delta = march_delta(o, n, o.maxVoxelIter / 2, invS);
+    const JobResult h = scene_distance<kCount>(s, V, n * d + pos, n, delta, o.maxVoxelIter / 2, invS, false);
+    ao *= 1.0f - cl_max((d - h.dist) * o.aoAmp / d, 0.0f);
   }
   return ao;
 }
 
 // renderer.cl:348-381 (shadow :292-301 inlined)
-RM_DEV float3 object_lighting(Scene& s, const PixelState& st, float3 rd, float3 ipos, const RmMaterial& m,
+template <bool kCount, class Vol>
+RM_DEV float3 object_lighting(Scene& s, const Vol& V, const PixelState& st, float3 rd, float3 ipos, const RmMaterial& m,
                               float3 n, float3 reflectCol) {
   const RmOpts& o = s.o;
-  const float ao = ambient_occlusion(s, ipos, n);
+  const float ao = ambient_occlusion<kCount>(s, V, ipos, n);
   float3 diff = sky(o, n) * ao;
   float3 spec = reflectCol * ao;
   float3 fin = f3s(0.0f);
@@ -203,7 +362,7 @@ RM_DEV float3 object_lighting(Scene& s, const PixelState& st, float3 rd, float3 
       const float3 ldir = unit3(dl);
       const float lmax = cl_min(sqrtf(ld2) - o.shadowBias, o.maxDist);
       Isec sh;
-      sphere_trace(s, ipos + ldir * o.shadowBias, ldir, sh, lmax, o.shadowIter, false);
+      sphere_trace<kCount>(s, V, ipos + ldir * o.shadowBias, ldir, sh, lmax, o.shadowIter, false, false);
       const float sf = sh.distance < lmax ? 0.0f : 1.0f;
       if (sf > 0.0f) {
         const float3 inc = (o.lightColor[i] * sf) * att;
@@ -220,24 +379,26 @@ RM_DEV float3 object_lighting(Scene& s, const PixelState& st, float3 rd, float3 
 RM_DEV int mat_index(int id) { return id < 0 ? 0 : (id > 3 ? 3 : id); }
 
 // renderer.cl:383-405
-RM_DEV float3 bounce_color(Scene& s, const PixelState& st, float3 ro, float3 rd, Isec& isec) {
+template <bool kCount, class Vol>
+RM_DEV float3 bounce_color(Scene& s, const Vol& V, const PixelState& st, float3 ro, float3 rd, Isec& isec) {
   const RmOpts& o = s.o;
-  sphere_trace(s, ro, rd, isec, o.maxDist, o.maxIter, false);
+  sphere_trace<kCount>(s, V, ro, rd, isec, o.maxDist, o.maxIter, false, true);
   float3 col;
   if (isec.objectID < 0) {
     col = sky(o, rd);
   } else {
-    col = object_lighting(s, st, rd, isec.pos, o.mat[mat_index(isec.objectID)], isec.normal,
-                          sky(o, reflect3(rd, isec.normal)));
+    col = object_lighting<kCount>(s, V, st, rd, isec.pos, o.mat[mat_index(isec.objectID)], isec.normal,
+                                  sky(o, reflect3(rd, isec.normal)));
   }
   return atmosphere(s, st, ro, rd, isec.distance, col);
 }
 
 // renderer.cl:407-446
-RM_DEV float3 scene_color(Scene& s, const PixelState& st, float3 ro, float3 rd) {
+template <bool kCount, class Vol>
+RM_DEV float3 scene_color(Scene& s, const Vol& V, const PixelState& st, float3 ro, float3 rd) {
   const RmOpts& o = s.o;
   Isec isec;
-  sphere_trace(s, ro, rd, isec, o.maxDist, o.maxIter, true);
+  sphere_trace<kCount>(s, V, ro, rd, isec, o.maxDist, o.maxIter, true, true);
   float3 col;
   if (isec.distance >= o.maxDist) {
     col = sky(o, rd);
@@ -253,14 +414,14 @@ RM_DEV float3 scene_color(Scene& s, const PixelState& st, float3 ro, float3 rd) 
       for (int i = 0; i < o.reflectIter; ++i) {
         bd = reflect3(bd, ri.normal);
         const float3 bo = ri.pos + bd * 0.0075f;
-        reflectCol = reflectCol + bounce_color(s, st, bo, bd, ri);
+        reflectCol = reflectCol + bounce_color<kCount>(s, V, st, bo, bd, ri);
         if (ri.objectID < 0) break;
         if (o.mat[mat_index(ri.objectID)].r0 < 0.001f) break;
       }
     } else {
       reflectCol = sky(o, reflect3(rd, n));
     }
-    col = object_lighting(s, st, rd, isec.pos, m, n, reflectCol);
+    col = object_lighting<kCount>(s, V, st, rd, isec.pos, m, n, reflectCol);
   }
   return atmosphere(s, st, ro, rd, isec.distance, col);
 }
@@ -282,10 +443,11 @@ RM_DEV float3 setup_pixel(const Scene& s, int id, PixelState& st) {
 }
 
 // One work-item of RenderImage (renderer.cl:478-494): returns sceneColor * exposure.
-RM_DEV float3 render_pixel_sample(Scene& s, int id) {
+template <bool kCount, class Vol>
+RM_DEV float3 render_pixel_sample(Scene& s, const Vol& V, int id) {
   PixelState st;
   const float3 rd = setup_pixel(s, id, st);
-  return scene_color(s, st, st.eye, rd) * s.o.exposure;
+  return scene_color<kCount>(s, V, st, st.eye, rd) * s.o.exposure;
 }
 
 }  // namespace plain

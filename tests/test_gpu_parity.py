@@ -187,11 +187,11 @@ def test_full_size_property_idempotent_and_deterministic(gpu_renderer):
 
 
 @pytest.mark.parametrize("knobs", [
-    {3: 2}, {3: 3}, {3: 4}, {4: 1, 5: 1}, {4: 4, 5: 32}, {4: 1000, 5: 1}, {6: 1}, {6: 2},
+    {3: 2}, {3: 3}, {3: 4}, {3: 5}, {6: 1}, {6: 2},
 ], ids=lambda k: "-".join(f"{a}={b}" for a, b in k.items()))
 def test_fast_kernel_tuning_knobs_do_not_change_results(gpu_renderer, knobs):
-    """Macro-cell size, march quota / leave threshold and the pass-fusion limit are scheduling
-    choices only: accumulator bits and work counters must not move."""
+    """Macro-cell size of the distance map and the pass-fusion limit are performance choices
+    only: accumulator bits and work counters must not move."""
     kw = dict(vres=96, width=120, height=72, iters=3, mat="metal")
     vol, opts, mcs = build_scene(**kw)
     gpu_renderer.set_option(2, 1)
@@ -203,7 +203,7 @@ def test_fast_kernel_tuning_knobs_do_not_change_results(gpu_renderer, knobs):
         px, _, cnt = render_gpu(gpu_renderer, vol, opts, mcs, 120, 72)
         px_nc, _, _ = render_gpu(gpu_renderer, vol, opts, mcs, 120, 72, count=False)
     finally:
-        for k, v in {3: 0, 4: 32, 5: 12, 6: 32}.items():
+        for k, v in {3: 0, 6: 32}.items():
             gpu_renderer.set_option(k, v)
     assert np.array_equal(cnt, cref)
     assert np.array_equal(px.view(np.uint32), ref.view(np.uint32))
