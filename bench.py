@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="fast", choices=["fast", "plain"])
+    ap.add_argument("--kernel", default="fast", choices=["fast", "plain", "warp"])
     ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE",
                     help="rm_set_option tuning knob of the fast kernel (results do not depend on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,7 +239,7 @@ def run_b200(args):
 
     layout = ShardLayout(w, h, world, *TILE)
     r = Renderer(local)
-    r.set_option(_lib.RM_OPT_KERNEL, 0 if args.kernel == "fast" else 1)
+    r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2}[args.kernel])
     for kv in args.opt:
         k, v = kv.split("=")
         r.set_option(int(k), int(v))
@@ -356,8 +356,9 @@ def run_b200(args):
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic(args.workload, args.kernel),
             "peak_source": peak_src,
-            "kernel": "k_render_fast (all passes of a frame in one launch)" if args.kernel == "fast"
-                      else "k_render_plain (one launch per pass)",
+            "kernel": {"fast": "k_render_bricks (all passes of a frame in one launch)",
+                       "warp": "k_render_warp (persistent, all passes of a frame in one launch)",
+                       "plain": "k_render_plain (one launch per pass)"}[args.kernel],
             "algorithmic_bytes_per_frame": steps_frame + taps_frame,
             "kernel_ms_per_frame": kernel_s_per_frame * 1e3,
             "kernel_share_of_step": kernel_s_per_frame * 1e3 / ms_per_step,

@@ -60,6 +60,10 @@ struct rm_ctx {
   float4* d_colour = nullptr;       // per-pass colours of one fused launch
   size_t colour_capacity = 0;       // float4 elements
   int num_sms = 0;
+  unsigned long long* d_queue = nullptr;  // work queue head of the warp kernel
+  unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
+  unsigned trip_limit = 1u << 28;
+  int warp_blocks[2] = {0, 0};            // resident blocks per SM of the warp kernel [plain, counting]
   int cell_shift_opt = 0;           // 0 = auto
   int fuse_limit = RM_MAX_FUSED_PASSES;
 
@@ -250,8 +254,20 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
       float times[RM_MAX_FUSED_PASSES], blend[RM_MAX_FUSED_PASSES];
       for (int k = 0; k < m; ++k) { times[k] = passes[i + k].time; blend[k] = passes[i + k].frameBlend; }
       EventPair t = begin_timed(c, 0);
-      cudaError_t e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
-                                            c->d_colour, c->d_accum, cnt, c->stream);
+      cudaError_t e;
+      if (c->kernel_kind == 2) {
+        const int variant = cnt ? 1 : 0;
+        if (!c->warp_blocks[variant]) c->warp_blocks[variant] = rm_warp_blocks_per_sm(variant);
+        if (c->warp_blocks[variant] <= 0) return fail(c, RM_ERR_CUDA, "warp render kernel does not fit on an SM");
+        e = rm_launch_render_warp(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, m, c->d_colour,
+                                  c->d_accum, c->d_queue, cnt, c->d_watchdog, c->trip_limit,
+                                  c->warp_blocks[variant] * c->num_sms, c->stream);
+        if (e == cudaSuccess && m > 1)
+          e = rm_launch_blend_passes(c->d_colour, blend, m, c->shard, c->W, c->H, c->d_accum, c->stream);
+      } else {
+        e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
+                                  c->d_colour, c->d_accum, cnt, c->stream);
+      }
       end_timed(c, t);
       if (e != cudaSuccess) return cuda_fail(c, e, "render kernel launch");
       c->stats.kernel_launches += m > 1 ? 2 : 1;
@@ -262,6 +278,22 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
   c->stats.pixel_samples += (uint64_t)rm_shard_pixels(c) * (uint64_t)n;
   if (c->pending.size() > 512) resolve_timers(c);
   return RM_OK;
+}
+
+// After a synchronisation point: did a warp of the warp kernel give up (watchdog)?
+int check_watchdog(rm_ctx* c) {
+  if (c->kernel_kind != 2) return RM_OK;
+  unsigned w[16];
+  RM_CUDA(c, cudaMemcpy(w, c->d_watchdog, sizeof w, cudaMemcpyDeviceToHost));
+  if (!w[0]) return RM_OK;
+  cudaMemset(c->d_watchdog, 0, sizeof w);
+  char msg[384];
+  std::snprintf(msg, sizeof msg,
+                "render kernel watchdog: a warp exceeded %u trips (lane state %u sub %u trace %u consumer %u rem %d iters %d "
+                "pixel %u item %u masks idle %08x march %08x job %08x shade %08x exhausted %u block %u thread %u)",
+                c->trip_limit, w[1], w[2], w[3], w[4], (int)w[5], (int)w[6], w[7], w[8], w[9], w[10], w[11], w[12], w[13],
+                w[14], w[15]);
+  return fail(c, RM_ERR_CUDA, msg);
 }
 
 int require_ready(rm_ctx* c) {
@@ -308,7 +340,10 @@ int rm_create(int device_id, rm_ctx** out_ctx) {
   if ((e = cudaSetDevice(device_id)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMalloc(&c->d_counters, sizeof(RmCounters))) != cudaSuccess ||
-      (e = cudaMemset(c->d_counters, 0, sizeof(RmCounters))) != cudaSuccess) {
+      (e = cudaMemset(c->d_counters, 0, sizeof(RmCounters))) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_queue, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_watchdog, 16 * sizeof(unsigned))) != cudaSuccess ||
+      (e = cudaMemset(c->d_watchdog, 0, 16 * sizeof(unsigned))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "rm_create");
     delete c;
     return rc;
@@ -327,7 +362,7 @@ void rm_destroy(rm_ctx* c) {
   resolve_timers(c);
   for (EventPair& p : c->free_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_tables); cudaFree(c->d_counters);
-  cudaFree(c->d_colour);
+  cudaFree(c->d_colour); cudaFree(c->d_queue); cudaFree(c->d_watchdog);
   rm_accel_free(&c->accel);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -410,7 +445,7 @@ int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, 
   c->stats.h2d_bytes += tbytes * iter + (size_t)RM_OPTS_BYTES * iter;
   if ((rc = launch_passes(c, dec.data(), iter, c->d_tables))) return rc;
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  return RM_OK;
+  return check_watchdog(c);
 }
 
 int rm_upload_passes(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
@@ -471,6 +506,7 @@ int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out)
   end_timed(c, t2);
   if (e != cudaSuccess) return cuda_fail(c, e, "argb read-back");
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  if ((rc = check_watchdog(c))) return rc;
   std::memcpy(argb_out, c->h_stage, n * sizeof(uint32_t));
   c->stats.d2h_bytes += n * sizeof(uint32_t);
   return RM_OK;
@@ -516,14 +552,14 @@ int rm_read_accum(rm_ctx* c, float* rgba_out) {
   RM_CUDA(c, cudaMemcpyAsync(rgba_out, c->d_accum, bytes, cudaMemcpyDeviceToHost, c->stream));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stats.d2h_bytes += bytes;
-  return RM_OK;
+  return check_watchdog(c);
 }
 
 int rm_sync(rm_ctx* c) {
   if (!c) return RM_ERR_INVALID_ARG;
   RM_CUDA(c, cudaSetDevice(c->device));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  return RM_OK;
+  return check_watchdog(c);
 }
 
 int rm_set_stream(rm_ctx* c, void* cuda_stream) {
@@ -563,13 +599,17 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
   switch (option) {
     case RM_OPT_COUNT_WORK: c->count_work = value != 0; return RM_OK;
     case RM_OPT_KERNEL:
-      if (value < 0 || value > 1) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_KERNEL: 0 (fast) or 1 (plain)");
+      if (value < 0 || value > 2) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_KERNEL: 0 (bricks), 1 (plain) or 2 (warp)");
       c->kernel_kind = (int)value;
       return RM_OK;
     case RM_OPT_CELL_SHIFT:
       if (value < 0 || value > 6 || value == 1) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_CELL_SHIFT: 0 (auto) or 2..6");
       c->cell_shift_opt = (int)value;
       c->accel.valid = false;
+      return RM_OK;
+    case RM_OPT_TRIP_LIMIT:
+      if (value < 1 || value > 0xffffffffLL) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_TRIP_LIMIT: 1..2^32-1");
+      c->trip_limit = (unsigned)value;
       return RM_OK;
     case RM_OPT_FUSE_LIMIT:
       if (value < 1 || value > RM_MAX_FUSED_PASSES) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_FUSE_LIMIT: 1..32");

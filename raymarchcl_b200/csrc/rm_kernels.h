@@ -50,3 +50,18 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
                                   const float4* d_tables, const float* times, const float* blend,
                                   int passes, float4* d_colour, float4* d_accum, RmCounters* d_counters,
                                   cudaStream_t stream);
+
+// pixels = mix(pixels, colour_k, blend_k) for k = 0..passes-1, in order (renderer.cl:492), from the
+// colour buffer of a fused launch (passes x slots float4).
+cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, int passes, const RmShard& shard,
+                                   int W, int H, float4* d_accum, cudaStream_t stream);
+
+// ---- warp-scheduled state machine (rm_render_warp.cu), RM_OPT_KERNEL = 2 ----
+int rm_warp_blocks_per_sm(int count);
+// Persistent launch over (pixel, pass) items; colours go to d_colour when passes > 1 (blend with
+// rm_launch_blend_passes afterwards), else straight into d_accum. d_watchdog: 16 words zeroed by
+// the caller; word 0 != 0 afterwards = a warp exceeded trip_limit trips and gave up.
+cudaError_t rm_launch_render_warp(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
+                                  const float4* d_tables, const float* times, int passes, float4* d_colour,
+                                  float4* d_accum, unsigned long long* d_queue, RmCounters* d_counters,
+                                  unsigned* d_watchdog, unsigned trip_limit, int grid_blocks, cudaStream_t stream);

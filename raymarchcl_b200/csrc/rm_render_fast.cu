@@ -15,7 +15,10 @@
 
 namespace {
 
-constexpr int kFastBlock = 128;
+#ifndef RM_FAST_BLOCK
+#define RM_FAST_BLOCK 128
+#endif
+constexpr int kFastBlock = RM_FAST_BLOCK;
 
 struct FastParams {
   const float4* tables;              // passes x 16384 float4
@@ -26,16 +29,27 @@ struct FastParams {
   int passes;
 };
 
+// 10 resident blocks of 128 threads per SM (48 registers per thread, a few spills to L1): the
+// kernel is latency- and issue-bound, not register-bound; measured on B200 (C2) 1 -> 6 -> 8 -> 10 -> 12
+// blocks: 178 -> 140 -> 124 -> 118 -> 116 ms per frame.
+#ifndef RM_FAST_MINBLOCKS
+#define RM_FAST_MINBLOCKS 10
+#endif
+
 template <bool kCount>
-__global__ void __launch_bounds__(kFastBlock)
+__global__ void __launch_bounds__(kFastBlock, RM_FAST_MINBLOCKS)
 k_render_bricks(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard sh,
                 const __grid_constant__ RmAccel acc, const __grid_constant__ FastParams P) {
   const long long item = (long long)blockIdx.x * kFastBlock + threadIdx.x;
   const long long total = (long long)P.passes * sh.slots;
   plain::Scene s(acc.vox, P.tables, o);
   if (item < total) {
-    const int pass = (int)(item / sh.slots);
-    const long long slot = item - (long long)pass * sh.slots;
+    // pass-minor item order: the lanes of a warp render the SAME pixels in different passes
+    // (32 / passes neighbouring pixels x all passes). Their rays differ only by the per-pass
+    // jitter, so they follow nearly the same control flow: far less divergence than 32
+    // different pixels of one pass.
+    const long long slot = item / P.passes;
+    const int pass = (int)(item - slot * P.passes);
     const int id = rm_slot_to_pixel(sh, slot, o.width, o.height);
     if (id >= 0) {
       s.time = P.times[pass];
@@ -43,7 +57,7 @@ k_render_bricks(const __grid_constant__ RmOpts o, const __grid_constant__ RmShar
       const plain::BrickVolume V{acc, (float)(1 << acc.cell_shift)};
       const float3 c = plain::render_pixel_sample<kCount>(s, V, id);
       if (P.colour) {
-        P.colour[item] = make_float4(c.x, c.y, c.z, 1.0f);
+        P.colour[item] = make_float4(c.x, c.y, c.z, 1.0f);  // [slot][pass]
       } else {
         const float4 old = P.accum[id];
         const float3 m = lerp3(f3(old.x, old.y, old.z), c, o.frameBlend);  // mix(), renderer.cl:492
@@ -80,7 +94,7 @@ k_blend_passes(const float4* __restrict__ colour, const __grid_constant__ BlendW
   const float4 old = accum[id];
   float3 p = f3(old.x, old.y, old.z);
   for (int k = 0; k < passes; ++k) {
-    const float4 c = __ldcs(colour + (size_t)k * sh.slots + slot);
+    const float4 c = __ldcs(colour + (size_t)slot * passes + k);
     p = lerp3(p, f3(c.x, c.y, c.z), bw.w[k]);
   }
   accum[id] = make_float4(p.x, p.y, p.z, 1.0f);
@@ -96,11 +110,7 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
   if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
   FastParams P;
   P.tables = d_tables;
-  BlendWeights bw;
-  for (int i = 0; i < RM_MAX_FUSED_PASSES; ++i) {
-    P.times[i] = i < passes ? times[i] : 0.0f;
-    bw.w[i] = i < passes ? blend[i] : 0.0f;
-  }
+  for (int i = 0; i < RM_MAX_FUSED_PASSES; ++i) P.times[i] = i < passes ? times[i] : 0.0f;
   P.colour = passes > 1 ? d_colour : nullptr;
   P.accum = d_accum;
   P.counters = d_counters;
@@ -114,10 +124,16 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
     k_render_bricks<false><<<(unsigned)blocks, kFastBlock, 0, stream>>>(opts, shard, accel, P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (passes > 1) {
-    k_blend_passes<<<(unsigned)((shard.slots + 255) / 256), 256, 0, stream>>>(d_colour, bw, passes, shard,
-                                                                            opts.width, opts.height, d_accum);
-    e = cudaGetLastError();
-  }
+  if (passes > 1) e = rm_launch_blend_passes(d_colour, blend, passes, shard, opts.width, opts.height, d_accum, stream);
   return e;
+}
+
+cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, int passes, const RmShard& shard,
+                                   int W, int H, float4* d_accum, cudaStream_t stream) {
+  if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
+  if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
+  BlendWeights bw;
+  for (int i = 0; i < RM_MAX_FUSED_PASSES; ++i) bw.w[i] = i < passes ? blend[i] : 0.0f;
+  k_blend_passes<<<(unsigned)((shard.slots + 255) / 256), 256, 0, stream>>>(d_colour, bw, passes, shard, W, H, d_accum);
+  return cudaGetLastError();
 }

@@ -82,8 +82,13 @@ struct ByteVolume {
 struct BrickVolume {
   const RmAccel& a;
   float cellf;
+  // brick / cell indices fit 32 bits (rm_set_volume bounds the grid), so index math stays 32-bit
   RM_DEV uint64_t word(const uint64_t* __restrict__ bricks, int x, int y, int z) const {
-    return __ldg(bricks + ((size_t)(z >> 2) * a.by + (y >> 2)) * a.bx + (x >> 2));
+    return __ldg(bricks + (unsigned)(((z >> 2) * a.by + (y >> 2)) * a.bx + (x >> 2)));
+  }
+  RM_DEV int cell_dist(int x, int y, int z) const {
+    const int cs = a.cell_shift;
+    return __ldg(a.dist + (unsigned)(((z >> cs) * a.my + (y >> cs)) * a.mx + (x >> cs)));
   }
   static RM_DEV unsigned bit(int x, int y, int z) { return (x & 3) | ((y & 3) << 2) | ((z & 3) << 4); }
   RM_DEV int value(const RmOpts& o, int x, int y, int z) const {
@@ -166,12 +171,11 @@ template <bool kCount>
 RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
   const RmOpts& o = s.o;
   const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
-  const int cs = V.a.cell_shift;
   while (rem > 0) {
     const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
     if (kCount) s.w.steps++;
     if (!in_grid(o, x, y, z)) return false;
-    const int d = __ldg(V.a.dist + ((size_t)(z >> cs) * V.a.my + (y >> cs)) * V.a.mx + (x >> cs));
+    const int d = V.cell_dist(x, y, z);
     if (d != 0) {
       // This sample and the next n-1 lie in cells known to hold no solid voxel: advance the
       // recurrence without fetching. n-1 further steps of at most 1/invS voxels each stay within
@@ -189,7 +193,11 @@ RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int r
           }
         }
       } else {
-        for (int j = 0; j < n; ++j) p = p + delta;
+        int j = 0;
+        for (; j + 4 <= n; j += 4) {
+          p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+        }
+        for (; j < n; ++j) p = p + delta;
       }
     } else {
       if ((V.word(V.a.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
@@ -200,9 +208,15 @@ RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int r
   return false;
 }
 
-// renderer.cl:209-237 without the normal
+// renderer.cl:209-237 without the normal. Deliberately NOT inlined: the four call sites (primary,
+// bounce and shadow sphere-traces, AO probes) then share one copy of the march loop, which cuts
+// the kernel's code size ~3x; measured on B200 (C2): 220 -> 178 ms per frame from this alone
+// (instruction-fetch stalls were the top stall reason), and it frees registers for occupancy.
+#ifndef RM_SD_INLINE
+#define RM_SD_INLINE __device__ __noinline__
+#endif
 template <bool kCount, class Vol>
-RM_DEV JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float3 dir, float3 delta, int steps, float invS,
+RM_SD_INLINE JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float3 dir, float3 delta, int steps, float invS,
                                 bool smooth) {
   const RmOpts& o = s.o;
   JobResult r;
@@ -244,8 +258,11 @@ RM_DEV float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
 }
 
 // renderer.cl:239-257
+#ifndef RM_ST_INLINE
+#define RM_ST_INLINE RM_DEV
+#endif
 template <bool kCount, class Vol>
-RM_DEV void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Isec& r, float maxDist, int maxSteps,
+RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Isec& r, float maxDist, int maxSteps,
                          bool smooth, bool wantSurface) {
   const RmOpts& o = s.o;
   float invS;
@@ -346,8 +363,11 @@ RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
 }
 
 // renderer.cl:348-381 (shadow :292-301 inlined)
+#ifndef RM_OL_INLINE
+#define RM_OL_INLINE RM_DEV
+#endif
 template <bool kCount, class Vol>
-RM_DEV float3 object_lighting(Scene& s, const Vol& V, const PixelState& st, float3 rd, float3 ipos, const RmMaterial& m,
+RM_OL_INLINE float3 object_lighting(Scene& s, const Vol& V, const PixelState& st, float3 rd, float3 ipos, const RmMaterial& m,
                               float3 n, float3 reflectCol) {
   const RmOpts& o = s.o;
   const float ao = ambient_occlusion<kCount>(s, V, ipos, n);

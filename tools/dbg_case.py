@@ -7,6 +7,7 @@ from oracle import refso, build_oracle
 build_oracle.build(verbose=False)
 orc = refso.load("oracle")
 r = Renderer(0)
+r.set_option(2, int(os.environ.get("KERNEL", "2")))
 r.set_option(7, int(os.environ.get("TRIPS", "2000000")))
 vres, w, h, it = [int(a) for a in sys.argv[1:5]]
 kw = dict(vres=vres, width=w, height=h, iters=it, mat="metal")
@@ -21,7 +22,3 @@ for count in (True, False):
     except Exception as e:
         print(os.environ.get("RAYMARCH_B200_LIB"), "count", count, "FAILED", e, flush=True)
         break
-    finally:
-        dbg = np.zeros(32, np.uint32)
-        r._lib.rm_debug_read(r._h, dbg.ctypes.data)
-        print("debug words", dbg[16:26].tolist(), flush=True)
