@@ -246,7 +246,7 @@ def run_b200(args):
     r.set_tile_shard(rank, world, *TILE)
     stream = torch.cuda.Stream(device=dev)
     r.set_stream(stream.cuda_stream)
-    gather = FrameGatherer(layout, rank, dev, torch.int32) if world > 1 else None
+    gather = FrameGatherer(layout, rank, dev, torch.int32, renderer=r) if world > 1 else None
     frame1 = torch.empty(w * h, dtype=torch.int32, device=dev) if world == 1 else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     argb_host = torch.empty(w * h, dtype=torch.int32).pin_memory()

@@ -127,6 +127,13 @@ int rm_set_stream(rm_ctx* ctx, void* cuda_stream);
 int rm_set_tile_shard(rm_ctx* ctx, int rank, int world, int tile_w, int tile_h);
 /* Number of pixels this context owns under the current shard and framebuffer. */
 int64_t rm_shard_pixels(const rm_ctx* ctx);
+/* Work slots (pixels + padding of edge tiles) of shard `rank` of `world` under the current
+ * framebuffer and tile size = the element count of that rank's packed buffer. Rank 0's is the largest. */
+int64_t rm_shard_slots(const rm_ctx* ctx, int rank, int world);
+/* After the one gather: de-interleave the `world` packed per-rank buffers (device memory,
+ * `stride_slots` elements apart, elem_bytes = 4 for ARGB words or 16 for float4 accumulators)
+ * into a full frame in device memory (width*height elements). */
+int rm_unpack_shards(rm_ctx* ctx, const void* d_parts, int world, int64_t stride_slots, int elem_bytes, void* d_frame);
 
 /* ---- options, stats ---- */
 int rm_set_option(rm_ctx* ctx, int option, int64_t value);

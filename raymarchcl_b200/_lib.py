@@ -28,7 +28,7 @@ EXPORTS = [
     "rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_set_volume",
     "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
     "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
-    "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_set_option", "rm_get_stats",
+    "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_shard_slots", "rm_unpack_shards", "rm_set_option", "rm_get_stats",
     "rm_reset_stats",
 ]
 
@@ -87,6 +87,9 @@ def load() -> C.CDLL:
     lib.rm_set_tile_shard.argtypes = [vp, ip, ip, ip, ip]
     lib.rm_shard_pixels.argtypes = [vp]
     lib.rm_shard_pixels.restype = C.c_int64
+    lib.rm_shard_slots.argtypes = [vp, ip, ip]
+    lib.rm_shard_slots.restype = C.c_int64
+    lib.rm_unpack_shards.argtypes = [vp, vp, ip, C.c_int64, ip, vp]
     lib.rm_set_option.argtypes = [vp, ip, C.c_int64]
     lib.rm_get_stats.argtypes = [vp, C.POINTER(RmStats)]
     lib.rm_reset_stats.argtypes = [vp]

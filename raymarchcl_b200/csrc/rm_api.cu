@@ -580,6 +580,27 @@ int rm_set_tile_shard(rm_ctx* c, int rank, int world, int tile_w, int tile_h) {
   return RM_OK;
 }
 
+int64_t rm_shard_slots(const rm_ctx* c, int rank, int world) {
+  if (!c || c->W <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
+  const long long tiles = (long long)c->shard.tiles_x * c->shard.tiles_y;
+  const long long owned = tiles > rank ? (tiles - rank + world - 1) / world : 0;
+  return owned * c->shard.tile_w * c->shard.tile_h;
+}
+
+int rm_unpack_shards(rm_ctx* c, const void* d_parts, int world, int64_t stride_slots, int elem_bytes, void* d_frame) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!d_parts || !d_frame || world <= 0 || (elem_bytes != 4 && elem_bytes != 16))
+    return fail(c, RM_ERR_INVALID_ARG, "rm_unpack_shards: null buffer, world <= 0 or element size not 4 / 16");
+  if (c->W <= 0) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  if (stride_slots < rm_shard_slots(c, 0, world))
+    return fail(c, RM_ERR_INVALID_ARG, "rm_unpack_shards: stride_slots smaller than the largest shard");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  cudaError_t e = rm_launch_unpack_shards(d_parts, world, stride_slots, elem_bytes, c->W, c->H, c->shard, d_frame, c->stream);
+  if (e != cudaSuccess) return cuda_fail(c, e, "unpack kernel launch");
+  c->stats.kernel_launches += 1;
+  return RM_OK;
+}
+
 int64_t rm_shard_pixels(const rm_ctx* c) {
   if (!c || c->W <= 0) return 0;
   const RmShard& s = c->shard;

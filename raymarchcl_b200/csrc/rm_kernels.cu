@@ -78,7 +78,40 @@ k_pack_accum(const float4* __restrict__ accum, int W, int H, const __grid_consta
   packed[slot] = id >= 0 ? accum[id] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// De-interleave the gathered per-rank packed buffers (parts[r][slot], r < world) into the frame.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_unpack_shards(const T* __restrict__ parts, int world, long long stride, int W, int H,
+                const __grid_constant__ RmShard sh0, T* __restrict__ frame) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int r = blockIdx.y;
+  RmShard sh = sh0;
+  sh.rank = r;
+  sh.world = world;
+  const long long tiles = (long long)sh.tiles_x * sh.tiles_y;
+  sh.owned_tiles = tiles > r ? (int)((tiles - r + world - 1) / world) : 0;
+  sh.slots = (long long)sh.owned_tiles * sh.tile_w * sh.tile_h;
+  if (i >= sh.slots) return;
+  const int id = rm_slot_to_pixel(sh, i, W, H);
+  if (id >= 0) frame[id] = parts[(size_t)r * stride + i];
+}
+
 }  // namespace
+
+cudaError_t rm_launch_unpack_shards(const void* d_parts, int world, long long stride_slots, int elem_bytes, int W, int H,
+                                    const RmShard& shard, void* d_frame, cudaStream_t stream) {
+  if (world <= 0 || stride_slots <= 0) return cudaErrorInvalidValue;
+  const dim3 grid((unsigned)((stride_slots + 255) / 256), (unsigned)world);
+  if (elem_bytes == 4)
+    k_unpack_shards<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t*>(d_parts), world, stride_slots, W, H,
+                                                        shard, static_cast<uint32_t*>(d_frame));
+  else if (elem_bytes == 16)
+    k_unpack_shards<float4><<<grid, 256, 0, stream>>>(static_cast<const float4*>(d_parts), world, stride_slots, W, H, shard,
+                                                      static_cast<float4*>(d_frame));
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
 
 cudaError_t rm_launch_render_plain(const uint8_t* d_vox, const float4* d_table, const RmOpts& opts,
                                    const RmShard& shard, float4* d_accum, RmCounters* d_counters,

@@ -34,6 +34,11 @@ cudaError_t rm_launch_tonemap(const float4* d_accum, float gamma, int W, int H, 
 cudaError_t rm_launch_pack_accum(const float4* d_accum, int W, int H, const RmShard& shard,
                                  float4* d_packed, cudaStream_t stream);
 
+// The one multi-GPU assembly step after the gather: parts[r][slot] (r < world, `stride_slots`
+// elements apart, elements of 4 (ARGB) or 16 (float4 accumulator) bytes) -> frame[pixel].
+cudaError_t rm_launch_unpack_shards(const void* d_parts, int world, long long stride_slots, int elem_bytes, int W, int H,
+                                    const RmShard& shard, void* d_frame, cudaStream_t stream);
+
 // ---- fast path (rm_accel.cu, rm_render_fast.cu) ----
 #define RM_MAX_FUSED_PASSES 32
 

@@ -88,39 +88,47 @@ def assemble_frame(parts, layout: ShardLayout, out=None):
 
 
 class FrameGatherer:
-    """Precomputed index maps + buffers for the one gather of a frame to ``dst``."""
+    """Buffers + index maps for the ONE collective of a frame: every rank contributes its packed
+    shard (``local``, ``max_slots`` elements, tile-major), ``dst`` receives them side by side and
+    de-interleaves them into the frame -- with the library's own unpack kernel
+    (``rm_unpack_shards``) when a :class:`Renderer` is given, with a torch index copy otherwise
+    (CPU / gloo tests)."""
 
-    def __init__(self, layout: ShardLayout, rank: int, device, dtype, dst: int = 0, elem_shape=()):
+    def __init__(self, layout: ShardLayout, rank: int, device, dtype, dst: int = 0, elem_shape=(), renderer=None):
         import torch
-        self.layout, self.rank, self.dst = layout, rank, dst
+        self.layout, self.rank, self.dst, self.renderer = layout, rank, dst, renderer
         self.max_slots = layout.max_slots
-        self.local = torch.zeros((self.max_slots,) + tuple(elem_shape), dtype=dtype, device=device)
-        self.parts: Optional[List] = None
+        self.elem_shape = tuple(elem_shape)
+        self.local = torch.zeros((self.max_slots,) + self.elem_shape, dtype=dtype, device=device)
+        self.parts = None
         self.frame = None
         if rank == dst:
-            self.parts = [torch.zeros_like(self.local) for _ in range(layout.world)]
-            self.frame = torch.zeros((layout.width * layout.height,) + tuple(elem_shape), dtype=dtype, device=device)
-            # one fused scatter: concatenated source positions -> pixel ids
-            src, dstpix = [], []
-            for r in range(layout.world):
-                idx = layout.slot_pixel_index(r)
-                v = np.nonzero(idx >= 0)[0]
-                src.append(v + r * self.max_slots)
-                dstpix.append(idx[v])
-            self._src = torch.from_numpy(np.concatenate(src)).to(device)
-            self._dst = torch.from_numpy(np.concatenate(dstpix)).to(device)
+            self.parts = torch.zeros((layout.world, self.max_slots) + self.elem_shape, dtype=dtype, device=device)
+            self.frame = torch.zeros((layout.width * layout.height,) + self.elem_shape, dtype=dtype, device=device)
+            if renderer is None:
+                src, dstpix = [], []
+                for r in range(layout.world):
+                    idx = layout.slot_pixel_index(r)
+                    v = np.nonzero(idx >= 0)[0]
+                    src.append(v + r * self.max_slots)
+                    dstpix.append(idx[v])
+                self._src = torch.from_numpy(np.concatenate(src)).to(device)
+                self._dst = torch.from_numpy(np.concatenate(dstpix)).to(device)
 
     def gather(self):
-        """Collective: every rank contributes ``self.local``; returns the flat frame on ``dst``."""
-        import torch
+        """Collective: returns the flat frame on ``dst`` (None elsewhere)."""
         import torch.distributed as dist
         if self.layout.world == 1:
-            stacked = self.local.unsqueeze(0)
+            self.parts[0].copy_(self.local)
         else:
-            dist.gather(self.local, self.parts if self.rank == self.dst else None, dst=self.dst)
+            dist.gather(self.local, list(self.parts.unbind(0)) if self.rank == self.dst else None, dst=self.dst)
             if self.rank != self.dst:
                 return None
-            stacked = torch.stack(self.parts)
-        flat = stacked.reshape((-1,) + tuple(self.local.shape[1:]))
-        self.frame[self._dst] = flat[self._src]
+        if self.renderer is not None:
+            elem_bytes = self.local.element_size() * int(np.prod(self.elem_shape, dtype=np.int64))
+            self.renderer.unpack_shards(self.parts.data_ptr(), self.layout.world, self.max_slots, elem_bytes,
+                                        self.frame.data_ptr())
+        else:
+            flat = self.parts.reshape((-1,) + self.elem_shape)
+            self.frame[self._dst] = flat[self._src]
         return self.frame

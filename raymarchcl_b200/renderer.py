@@ -144,6 +144,14 @@ class Renderer:
     def shard_pixels(self) -> int:
         return int(self._lib.rm_shard_pixels(self._h))
 
+    def shard_slots(self, rank: int, world: int) -> int:
+        return int(self._lib.rm_shard_slots(self._h, int(rank), int(world)))
+
+    def unpack_shards(self, parts_dptr: int, world: int, stride_slots: int, elem_bytes: int, frame_dptr: int) -> None:
+        """De-interleave gathered per-rank packed buffers into a frame (all device memory)."""
+        self._check(self._lib.rm_unpack_shards(self._h, C.c_void_p(parts_dptr), int(world), int(stride_slots),
+                                               int(elem_bytes), C.c_void_p(frame_dptr)))
+
     def set_option(self, option: int, value: int) -> None:
         self._check(self._lib.rm_set_option(self._h, int(option), int(value)))
 

@@ -226,3 +226,51 @@ def test_fast_kernel_iso_boundary_and_non_uniform_passes(gpu_renderer, oracle):
     px, argb, cnt = render_gpu(gpu_renderer, vol, opts, mcs, 96, 64)
     assert np.array_equal(cnt, ref_cnt)
     check_frame(px, ref_px, argb, oracle.tonemap(ref_px, opts[0]))
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_packed_shards_unpack_to_the_full_frame(gpu_renderer, world):
+    """rm_tonemap_device / rm_copy_accum_device (packed) per shard + rm_unpack_shards = the frame an
+    unsharded context renders: the multi-GPU assembly step, exercised on one GPU."""
+    import torch
+    w, h = 150, 90
+    kw = dict(vres=64, width=w, height=h, iters=2, mat="metal")
+    vol, opts, mcs = build_scene(**kw)
+    gpu_renderer.set_option(2, 0)
+    full, argb_full, _ = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=False)
+    r = gpu_renderer
+    r.set_tile_shard(0, world, 32, 32)
+    r.clear_accum(w, h)
+    stride = r.shard_slots(0, world)
+    parts = torch.zeros((world, stride), dtype=torch.int32, device="cuda:0")
+    parts_acc = torch.zeros((world, stride, 4), dtype=torch.float32, device="cuda:0")
+    frame = torch.zeros(w * h, dtype=torch.int32, device="cuda:0")
+    frame_acc = torch.zeros((w * h, 4), dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()
+    for rank in range(world):
+        r.set_tile_shard(rank, world, 32, 32)
+        assert r.shard_slots(rank, world) <= stride
+        r.clear_accum(w, h)
+        r.render_frame(opts, mcs)
+        r.tonemap_device(opts[0], parts[rank].data_ptr(), packed=True)
+        r.copy_accum_device(parts_acc[rank].data_ptr(), packed=True)
+    r.unpack_shards(parts.data_ptr(), world, stride, 4, frame.data_ptr())
+    r.unpack_shards(parts_acc.data_ptr(), world, stride, 16, frame_acc.data_ptr())
+    r.sync()
+    r.set_tile_shard(0, 1, 32, 32)
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32).reshape(h, w), argb_full)
+    assert np.array_equal(frame_acc.cpu().numpy().reshape(h, w, 4).view(np.uint32), full.view(np.uint32))
+
+
+def test_warp_scheduled_kernel_matches_oracle(gpu_renderer, oracle):
+    """RM_OPT_KERNEL = 2 (persistent warp-scheduled state machine): same results, exact counters."""
+    kw = dict(vres=128, width=200, height=120, iters=2, mat="metal2", dof=0.025)
+    vol, opts, mcs = build_scene(**kw)
+    ref_px, ref_cnt = oracle.render_frame(vol, mcs, opts, 200, 120)
+    gpu_renderer.set_option(2, 2)
+    try:
+        px, argb, cnt = render_gpu(gpu_renderer, vol, opts, mcs, 200, 120)
+    finally:
+        gpu_renderer.set_option(2, 0)
+    assert np.array_equal(cnt, ref_cnt)
+    check_frame(px, ref_px, argb, oracle.tonemap(ref_px, opts[0]))
