@@ -234,8 +234,11 @@ def run_b200(args):
     sc = wl["scene"]
     w, h, iters = sc["width"], sc["height"], sc["iters"]
     vol, opts, mcs = build_scene(**sc)
+    # host-side inputs of the end-to-end arm live in pinned memory
     vol_pinned = torch.from_numpy(np.ascontiguousarray(vol)).pin_memory()
     vol_host = vol_pinned.numpy()
+    mcs_pinned = [torch.from_numpy(np.ascontiguousarray(m)).pin_memory() for m in mcs]
+    mcs_host = [m.numpy() for m in mcs_pinned]
 
     layout = ShardLayout(w, h, world, *TILE)
     r = Renderer(local)
@@ -313,7 +316,7 @@ def run_b200(args):
             def host_frame():
                 r.set_volume(vol_host)
                 r.clear_accum(w, h)
-                r.render_frame(opts, mcs)
+                r.render_frame(opts, mcs_host)
                 if world == 1:
                     return r.tonemap(opts[0], out=argb_host.numpy().view(np.uint32))
                 r.tonemap_device(opts[0], gather.local.data_ptr(), packed=True)

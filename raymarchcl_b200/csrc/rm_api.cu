@@ -30,6 +30,7 @@ struct rm_ctx {
 
   // volume ("v-buf")
   uint8_t* d_vox = nullptr;
+  size_t vox_capacity = 0;
   int rx = 0, ry = 0, rz = 0;
 
   // framebuffer ("p-buf", "q-buf")
@@ -43,10 +44,6 @@ struct rm_ctx {
   int table_capacity = 0;
   std::vector<RmOpts> passes;  // decoded resident opts
   int resident = 0;            // passes uploaded by rm_upload_passes
-
-  // pinned staging
-  void* h_stage = nullptr;
-  size_t h_stage_bytes = 0;
 
   RmShard shard{};
   int shard_rank = 0, shard_world = 1, shard_tw = 32, shard_th = 32;
@@ -148,15 +145,6 @@ void update_shard(rm_ctx* c) {
   const long long tiles = (long long)s.tiles_x * s.tiles_y;
   s.owned_tiles = tiles > s.rank ? (int)((tiles - s.rank + s.world - 1) / s.world) : 0;
   s.slots = (long long)s.owned_tiles * s.tile_w * s.tile_h;
-}
-
-int ensure_stage(rm_ctx* c, size_t bytes) {
-  if (c->h_stage_bytes >= bytes) return RM_OK;
-  if (c->h_stage) cudaFreeHost(c->h_stage);
-  c->h_stage = nullptr; c->h_stage_bytes = 0;
-  RM_CUDA(c, cudaMallocHost(&c->h_stage, bytes));
-  c->h_stage_bytes = bytes;
-  return RM_OK;
 }
 
 int ensure_tables(rm_ctx* c, int n) {
@@ -364,7 +352,6 @@ void rm_destroy(rm_ctx* c) {
   cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_tables); cudaFree(c->d_counters);
   cudaFree(c->d_colour); cudaFree(c->d_queue); cudaFree(c->d_watchdog);
   rm_accel_free(&c->accel);
-  if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -375,9 +362,13 @@ int rm_set_volume(rm_ctx* c, const uint8_t* voxels, int rx, int ry, int rz) {
   if ((long long)rx * ry > 0x7fffffffLL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: rx*ry overflows int (voxelRes.w)");
   RM_CUDA(c, cudaSetDevice(c->device));
   const size_t bytes = (size_t)rx * ry * rz;
-  RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; }
-  RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
+  if (bytes / 64 > 0x7fffffffULL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: more than 2^37 voxels");
+  if (bytes > c->vox_capacity) {  // the allocation is kept across re-uploads (the reference re-uploads every frame)
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
+    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
+    c->vox_capacity = bytes;
+  }
   EventPair t = begin_timed(c, 2);
   cudaError_t e = cudaMemcpyAsync(c->d_vox, voxels, bytes, cudaMemcpyHostToDevice, c->stream);
   end_timed(c, t);
@@ -433,13 +424,12 @@ int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, 
   }
   const size_t tbytes = (size_t)RM_TABLE_FLOATS * sizeof(float);
   if ((rc = ensure_tables(c, iter > c->resident ? iter : c->resident))) return rc;
-  if ((rc = ensure_stage(c, tbytes * iter))) return rc;
   // a frame rendered from host buffers replaces any resident passes
   c->resident = 0;
-  RM_CUDA(c, cudaStreamSynchronize(c->stream));  // staging buffer reuse
-  for (int i = 0; i < iter; ++i) std::memcpy(static_cast<char*>(c->h_stage) + tbytes * i, mc[i], tbytes);
   EventPair t = begin_timed(c, 2);
-  cudaError_t e = cudaMemcpyAsync(c->d_tables, c->h_stage, tbytes * iter, cudaMemcpyHostToDevice, c->stream);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < iter && e == cudaSuccess; ++i)  // straight from the caller's (ideally pinned) buffers
+    e = cudaMemcpyAsync(c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4), mc[i], tbytes, cudaMemcpyHostToDevice, c->stream);
   end_timed(c, t);
   if (e != cudaSuccess) return cuda_fail(c, e, "table upload");
   c->stats.h2d_bytes += tbytes * iter + (size_t)RM_OPTS_BYTES * iter;
@@ -494,20 +484,18 @@ int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out)
   decode_opts(opts, &o);
   if (o.width != c->W || o.height != c->H) return fail(c, RM_ERR_BAD_OPTS, "rm_tonemap: TRenderOpts.resolution does not match the framebuffer");
   const size_t n = (size_t)c->W * c->H;
-  int rc = ensure_stage(c, n * sizeof(uint32_t));
-  if (rc) return rc;
+  int rc;
   EventPair t = begin_timed(c, 1);
   cudaError_t e = rm_launch_tonemap(c->d_accum, o.gamma, c->W, c->H, c->shard, c->d_argb, 0, c->stream);
   end_timed(c, t);
   if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
   c->stats.kernel_launches += 1;
   EventPair t2 = begin_timed(c, 3);
-  e = cudaMemcpyAsync(c->h_stage, c->d_argb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  e = cudaMemcpyAsync(argb_out, c->d_argb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   end_timed(c, t2);
   if (e != cudaSuccess) return cuda_fail(c, e, "argb read-back");
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   if ((rc = check_watchdog(c))) return rc;
-  std::memcpy(argb_out, c->h_stage, n * sizeof(uint32_t));
   c->stats.d2h_bytes += n * sizeof(uint32_t);
   return RM_OK;
 }
