@@ -167,13 +167,13 @@ RM_DEV bool march(Scene& s, const ByteVolume& V, float3& p, float3 delta, int st
   return false;
 }
 
-template <bool kCount>
-RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
+// Counting form: visits every sample the reference fetches (exact step counter).
+RM_DEV bool march_counting(Scene& s, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
   const RmOpts& o = s.o;
   const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
   while (rem > 0) {
     const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
-    if (kCount) s.w.steps++;
+    s.w.steps++;
     if (!in_grid(o, x, y, z)) return false;
     const int d = V.cell_dist(x, y, z);
     if (d != 0) {
@@ -184,20 +184,12 @@ RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int r
       int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
       n = n < rem ? n : rem;
       rem -= n;
-      if (kCount) {
-        for (int j = 1; j <= n; ++j) {
-          p = p + delta;
-          if (j < n) {  // the reference fetches (and counts) every one of these samples
-            s.w.steps++;
-            if (!in_grid(o, f2i_sat(p.x * rxf), f2i_sat(p.y * ryf), f2i_sat(p.z * rzf))) return false;
-          }
+      for (int j = 1; j <= n; ++j) {
+        p = p + delta;
+        if (j < n) {  // the reference fetches (and counts) every one of these samples
+          s.w.steps++;
+          if (!in_grid(o, f2i_sat(p.x * rxf), f2i_sat(p.y * ryf), f2i_sat(p.z * rzf))) return false;
         }
-      } else {
-        int j = 0;
-        for (; j + 4 <= n; j += 4) {
-          p = p + delta; p = p + delta; p = p + delta; p = p + delta;
-        }
-        for (; j < n; ++j) p = p + delta;
       }
     } else {
       if ((V.word(V.a.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
@@ -206,6 +198,41 @@ RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int r
     }
   }
   return false;
+}
+
+// Production form: the same walk without the per-sample bookkeeping of the counting form. Samples
+// known to be empty cost three adds each (the fp32 recurrence p += delta is part of the result:
+// the position of a hit feeds the next sphere-trace step) and no fetch.
+// (Tried and measured slower, 153 vs 104 ms per C2 frame: deferring the adds until a hit needs
+// them, locating samples approximately at p + k*delta meanwhile -- the extra per-lookup work and
+// the long catch-up loops at low lane counts cost more than the adds saved on missing rays.)
+RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
+  const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
+  while (rem > 0) {
+    const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
+    if (!in_grid(o, x, y, z)) return false;
+    const int d = V.cell_dist(x, y, z);
+    if (d != 0) {
+      const float reach = (float)(d - 1) * V.cellf - 0.25f;
+      int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
+      n = n < rem ? n : rem;
+      rem -= n;
+      int j = 0;
+      for (; j + 4 <= n; j += 4) { p = p + delta; p = p + delta; p = p + delta; p = p + delta; }
+      for (; j < n; ++j) p = p + delta;
+    } else {
+      if ((V.word(V.a.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
+      p = p + delta;
+      rem -= 1;
+    }
+  }
+  return false;
+}
+
+template <bool kCount>
+RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
+  if (kCount) return march_counting(s, V, p, delta, rem, invS);
+  return march_fast(s.o, V, p, delta, rem, invS);
 }
 
 // renderer.cl:209-237 without the normal. Deliberately NOT inlined: the four call sites (primary,

@@ -274,3 +274,23 @@ def test_warp_scheduled_kernel_matches_oracle(gpu_renderer, oracle):
         gpu_renderer.set_option(2, 0)
     assert np.array_equal(cnt, ref_cnt)
     check_frame(px, ref_px, argb, oracle.tonemap(ref_px, opts[0]))
+
+
+@pytest.mark.parametrize("kw", SCENES + [
+    dict(vres=192, width=96, height=64, iters=2, mat="metal", theta=20.0, dist=1.4),    # camera close to the box
+    dict(vres=256, width=64, height=64, iters=1, mat="metal2", theta=200.0, dist=0.6),  # camera INSIDE the box
+    dict(vres=100, width=80, height=50, iters=1, mat="ao", volume="terrain", theta=90.0),
+], ids=lambda k: f"{k.get('volume', 'gyroid')}{k['vres']}_{k['mat']}_{k['width']}x{k['height']}")
+def test_production_mode_equals_counting_mode_and_oracle(gpu_renderer, oracle, kw):
+    """The non-counting kernels skip empty samples without looking at them (march_fast); the counting
+    kernels visit every sample. Both must give the oracle's accumulator: bit-identical to each other."""
+    vol, opts, mcs = build_scene(**kw)
+    w, h = kw["width"], kw["height"]
+    ref_px, ref_cnt = oracle.render_frame(vol, mcs, opts, w, h)
+    gpu_renderer.set_option(2, 0)
+    a, argb_a, cnt = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=True)
+    b, argb_b, _ = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=False)
+    assert np.array_equal(cnt, ref_cnt)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(argb_a, argb_b)
+    check_frame(b, ref_px, argb_b, oracle.tonemap(ref_px, opts[0]))
