@@ -12,10 +12,10 @@ constexpr int kPlainBlock = 128;
 template <bool kCount>
 __global__ void __launch_bounds__(kPlainBlock)
 k_render_plain(const uint8_t* __restrict__ vox, const float4* __restrict__ table,
-               const __grid_constant__ RmOpts o, const __grid_constant__ RmShard sh,
-               float4* __restrict__ accum, RmCounters* __restrict__ counters) {
+               const __grid_constant__ RmShard sh, float4* __restrict__ accum, RmCounters* __restrict__ counters) {
+  const RmOpts& o = plain::g_opts;
   const long long slot = (long long)blockIdx.x * kPlainBlock + threadIdx.x;
-  plain::Scene s(vox, table, o);
+  plain::Scene s(vox, table);
   if (slot < sh.slots) {
     const int id = rm_slot_to_pixel(sh, slot, o.width, o.height);
     if (id >= 0) {
@@ -118,10 +118,12 @@ cudaError_t rm_launch_render_plain(const uint8_t* d_vox, const float4* d_table, 
                                    cudaStream_t stream) {
   if (shard.slots <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((shard.slots + kPlainBlock - 1) / kPlainBlock);
+  cudaError_t e = cudaMemcpyToSymbolAsync(plain::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
   if (d_counters)
-    k_render_plain<true><<<blocks, kPlainBlock, 0, stream>>>(d_vox, d_table, opts, shard, d_accum, d_counters);
+    k_render_plain<true><<<blocks, kPlainBlock, 0, stream>>>(d_vox, d_table, shard, d_accum, d_counters);
   else
-    k_render_plain<false><<<blocks, kPlainBlock, 0, stream>>>(d_vox, d_table, opts, shard, d_accum, nullptr);
+    k_render_plain<false><<<blocks, kPlainBlock, 0, stream>>>(d_vox, d_table, shard, d_accum, nullptr);
   return cudaGetLastError();
 }
 

@@ -38,11 +38,11 @@ struct FastParams {
 
 template <bool kCount>
 __global__ void __launch_bounds__(kFastBlock, RM_FAST_MINBLOCKS)
-k_render_bricks(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard sh,
-                const __grid_constant__ RmAccel acc, const __grid_constant__ FastParams P) {
+k_render_bricks(const __grid_constant__ RmShard sh, const __grid_constant__ FastParams P) {
+  const RmOpts& o = plain::g_opts;
   const long long item = (long long)blockIdx.x * kFastBlock + threadIdx.x;
   const long long total = (long long)P.passes * sh.slots;
-  plain::Scene s(acc.vox, P.tables, o);
+  plain::Scene s(plain::g_accel.vox, P.tables);
   if (item < total) {
     // pass-minor item order: the lanes of a warp render the SAME pixels in different passes
     // (32 / passes neighbouring pixels x all passes). Their rays differ only by the per-pass
@@ -54,7 +54,7 @@ k_render_bricks(const __grid_constant__ RmOpts o, const __grid_constant__ RmShar
     if (id >= 0) {
       s.time = P.times[pass];
       s.table = P.tables + (size_t)pass * (RM_TABLE_MASK + 1);
-      const plain::BrickVolume V{acc, (float)(1 << acc.cell_shift)};
+      const plain::BrickVolume V{};
       const float3 c = plain::render_pixel_sample<kCount>(s, V, id);
       if (P.colour) {
         P.colour[item] = make_float4(c.x, c.y, c.z, 1.0f);  // [slot][pass]
@@ -118,11 +118,14 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
   const long long total = (long long)passes * shard.slots;
   const long long blocks = (total + kFastBlock - 1) / kFastBlock;
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyToSymbolAsync(plain::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbolAsync(plain::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
   if (d_counters)
-    k_render_bricks<true><<<(unsigned)blocks, kFastBlock, 0, stream>>>(opts, shard, accel, P);
+    k_render_bricks<true><<<(unsigned)blocks, kFastBlock, 0, stream>>>(shard, P);
   else
-    k_render_bricks<false><<<(unsigned)blocks, kFastBlock, 0, stream>>>(opts, shard, accel, P);
-  cudaError_t e = cudaGetLastError();
+    k_render_bricks<false><<<(unsigned)blocks, kFastBlock, 0, stream>>>(shard, P);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (passes > 1) e = rm_launch_blend_passes(d_colour, blend, passes, shard, opts.width, opts.height, d_accum, stream);
   return e;

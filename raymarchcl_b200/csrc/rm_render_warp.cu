@@ -121,7 +121,7 @@ RM_DEV void trace_begin(Lane& L, const RmOpts& o, int kind, float3 ro, float3 rd
 
 // ambientOcclusion loop head (renderer.cl:333-336): next probe, or on to the lights
 RM_DEV void ao_next(Lane& L, const Scene& s) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = plain::g_opts;
   if (L.aoI <= o.aoIter && L.ao > 0.01f) {
     L.aoD += o.aoStepDist;
     L.aoSeed += 37u;
@@ -346,14 +346,15 @@ RM_DEV void job_step(Lane& L, Scene& s, const Ctx& C) {
 
 template <bool kCount>
 __global__ void __launch_bounds__(kWarpBlock)
-k_render_warp(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard sh,
-              const __grid_constant__ RmAccel acc, const __grid_constant__ WarpParams P) {
+k_render_warp(const __grid_constant__ RmShard sh, const __grid_constant__ WarpParams P) {
+  const RmOpts& o = plain::g_opts;
+  const RmAccel& acc = plain::g_accel;
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const long long total = (long long)P.passes * sh.slots;
-  const BrickVolume V{acc, (float)(1 << acc.cell_shift)};
+  const BrickVolume V{};
   const Ctx C{o, V, (float)o.rx, (float)o.ry, (float)o.rz};
-  Scene s(acc.vox, P.tables, o);
+  Scene s(acc.vox, P.tables);
   Lane L = {};
   L.state = S_IDLE;
   bool exhausted = false;
@@ -398,7 +399,7 @@ k_render_warp(const __grid_constant__ RmOpts o, const __grid_constant__ RmShard 
             const int d = V.cell_dist(x, y, z);
             if (d != 0) {
               // this sample and the next n-1 cannot be solid (see BrickVolume march)
-              const float reach = (float)(d - 1) * V.cellf - 0.25f;
+              const float reach = (float)(d - 1) * acc.cellf - 0.25f;
               int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * L.invS, 1e6f)) : 1;
               n = n < L.rem ? n : L.rem;
               L.rem -= n;
@@ -526,9 +527,11 @@ cudaError_t rm_launch_render_warp(const RmOpts& opts, const RmShard& shard, cons
   const long long total = (long long)passes * shard.slots;
   const long long need = (total + kWarpBlock - 1) / kWarpBlock;
   const unsigned blocks = (unsigned)(need < grid_blocks ? need : grid_blocks);
+  if ((e = cudaMemcpyToSymbolAsync(plain::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbolAsync(plain::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
   if (d_counters)
-    k_render_warp<true><<<blocks, kWarpBlock, 0, stream>>>(opts, shard, accel, P);
+    k_render_warp<true><<<blocks, kWarpBlock, 0, stream>>>(shard, P);
   else
-    k_render_warp<false><<<blocks, kWarpBlock, 0, stream>>>(opts, shard, accel, P);
+    k_render_warp<false><<<blocks, kWarpBlock, 0, stream>>>(shard, P);
   return cudaGetLastError();
 }

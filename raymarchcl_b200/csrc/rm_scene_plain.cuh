@@ -20,6 +20,16 @@
 
 namespace plain {
 
+// Per-launch constants. They live in __constant__ memory (one copy per translation unit that
+// includes this header; each launcher uploads them on its stream right before the launch) rather
+// than in kernel parameters, because the shared, NON-inlined distanceToScene below can then read
+// them as constant-bank operands; through a reference to a kernel parameter it had to re-load
+// them with generic loads on every march iteration (the register budget leaves no room to keep
+// them). Consequence: two contexts must not render concurrently on the SAME device from
+// different streams (documented in include/raymarch_b200.h, Threading).
+static __constant__ RmOpts g_opts;
+static __constant__ RmAccel g_accel;
+
 struct Work {  // reference-equivalent work counters of this thread
   unsigned steps, taps, outer;
 };
@@ -27,10 +37,9 @@ struct Work {  // reference-equivalent work counters of this thread
 struct Scene {
   const uint8_t* __restrict__ vox;
   const float4* __restrict__ table;
-  const RmOpts& o;
   float time;  // TRenderOpts.time of the pass this thread renders (per lane in the fused kernel)
   Work w;
-  RM_DEV Scene(const uint8_t* v, const float4* t, const RmOpts& opts) : vox(v), table(t), o(opts), time(opts.time) {
+  RM_DEV Scene(const uint8_t* v, const float4* t) : vox(v), table(t), time(g_opts.time) {
     w.steps = w.taps = w.outer = 0;
   }
 };
@@ -79,24 +88,22 @@ struct ByteVolume {
   }
 };
 
-struct BrickVolume {
-  const RmAccel& a;
-  float cellf;
+struct BrickVolume {  // stateless: everything comes from g_accel
   // brick / cell indices fit 32 bits (rm_set_volume bounds the grid), so index math stays 32-bit
   RM_DEV uint64_t word(const uint64_t* __restrict__ bricks, int x, int y, int z) const {
-    return __ldg(bricks + (unsigned)(((z >> 2) * a.by + (y >> 2)) * a.bx + (x >> 2)));
+    return __ldg(bricks + (unsigned)(((z >> 2) * g_accel.by + (y >> 2)) * g_accel.bx + (x >> 2)));
   }
   RM_DEV int cell_dist(int x, int y, int z) const {
-    const int cs = a.cell_shift;
-    return __ldg(a.dist + (unsigned)(((z >> cs) * a.my + (y >> cs)) * a.mx + (x >> cs)));
+    const int cs = g_accel.cell_shift;
+    return __ldg(g_accel.dist + (unsigned)(((z >> cs) * g_accel.my + (y >> cs)) * g_accel.mx + (x >> cs)));
   }
   static RM_DEV unsigned bit(int x, int y, int z) { return (x & 3) | ((y & 3) << 2) | ((z & 3) << 4); }
   RM_DEV int value(const RmOpts& o, int x, int y, int z) const {
-    return __ldg(a.vox + ((size_t)z * o.rxy + (size_t)y * o.rx + x));
+    return __ldg(g_accel.vox + ((size_t)z * o.rxy + (size_t)y * o.rx + x));
   }
   RM_DEV int occ(const RmOpts& o, int x, int y, int z) const {
     if (!in_grid(o, x, y, z)) return 0;
-    return (int)((word(a.occ, x, y, z) >> bit(x, y, z)) & 1ull);
+    return (int)((word(g_accel.occ, x, y, z) >> bit(x, y, z)) & 1ull);
   }
 };
 
@@ -156,7 +163,7 @@ struct JobResult {
 // sample position of the hit.
 template <bool kCount>
 RM_DEV bool march(Scene& s, const ByteVolume& V, float3& p, float3 delta, int steps, float) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   while (--steps >= 0) {
     const int x = f2i_sat(p.x * (float)o.rx), y = f2i_sat(p.y * (float)o.ry), z = f2i_sat(p.z * (float)o.rz);
     if (kCount) s.w.steps++;
@@ -169,7 +176,7 @@ RM_DEV bool march(Scene& s, const ByteVolume& V, float3& p, float3 delta, int st
 
 // Counting form: visits every sample the reference fetches (exact step counter).
 RM_DEV bool march_counting(Scene& s, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
   while (rem > 0) {
     const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
@@ -180,7 +187,7 @@ RM_DEV bool march_counting(Scene& s, const BrickVolume& V, float3& p, float3 del
       // This sample and the next n-1 lie in cells known to hold no solid voxel: advance the
       // recurrence without fetching. n-1 further steps of at most 1/invS voxels each stay within
       // (d-1) cells; 0.25 voxel of slack covers the rounding drift of the recurrence.
-      const float reach = (float)(d - 1) * V.cellf - 0.25f;
+      const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
       int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
       n = n < rem ? n : rem;
       rem -= n;
@@ -192,7 +199,7 @@ RM_DEV bool march_counting(Scene& s, const BrickVolume& V, float3& p, float3 del
         }
       }
     } else {
-      if ((V.word(V.a.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
+      if ((V.word(g_accel.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
       p = p + delta;
       rem -= 1;
     }
@@ -213,15 +220,20 @@ RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 
     if (!in_grid(o, x, y, z)) return false;
     const int d = V.cell_dist(x, y, z);
     if (d != 0) {
-      const float reach = (float)(d - 1) * V.cellf - 0.25f;
+      const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
       int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
       n = n < rem ? n : rem;
       rem -= n;
-      int j = 0;
-      for (; j + 4 <= n; j += 4) { p = p + delta; p = p + delta; p = p + delta; p = p + delta; }
-      for (; j < n; ++j) p = p + delta;
+      // n sequential adds, binary-decomposed so that short skips (the common case) take no loop
+      for (; n >= 8; n -= 8) {
+        p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+        p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+      }
+      if (n & 4) { p = p + delta; p = p + delta; p = p + delta; p = p + delta; }
+      if (n & 2) { p = p + delta; p = p + delta; }
+      if (n & 1) p = p + delta;
     } else {
-      if ((V.word(V.a.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
+      if ((V.word(g_accel.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
       p = p + delta;
       rem -= 1;
     }
@@ -232,7 +244,7 @@ RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 
 template <bool kCount>
 RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
   if (kCount) return march_counting(s, V, p, delta, rem, invS);
-  return march_fast(s.o, V, p, delta, rem, invS);
+  return march_fast(g_opts, V, p, delta, rem, invS);
 }
 
 // renderer.cl:209-237 without the normal. Deliberately NOT inlined: the four call sites (primary,
@@ -245,7 +257,7 @@ RM_DEV bool march(Scene& s, const BrickVolume& V, float3& p, float3 delta, int r
 template <bool kCount, class Vol>
 RM_SD_INLINE JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float3 dir, float3 delta, int steps, float invS,
                                 bool smooth) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   JobResult r;
   r.g = rpos.y + o.groundY;
   r.dist = r.g < 1e5f ? r.g : 1e5f;
@@ -256,7 +268,13 @@ RM_SD_INLINE JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float
                       rpos.y < o.boundsMax.y && rpos.z > o.boundsMin.z && rpos.z < o.boundsMax.z;
   // strictly inside: every entry quotient is < 0 and every exit quotient > 0, so the slab test
   // returns max(..., 0) = +0 without evaluating the divisions
-  const float idist = inside ? 0.0f : box_entry(o.boundsMin, o.boundsMax, rpos, dir);
+  // strictly beyond one slab and moving away from it: both quotients of that axis are negative,
+  // so the exit distance is negative and the test returns -1 (also when another axis yields
+  // NaN: OpenCL's min/max as written in rm_math.cuh then keep the negative operand)
+  const bool away = (rpos.x > o.boundsMax.x && dir.x > 0.0f) || (rpos.x < o.boundsMin.x && dir.x < 0.0f) ||
+                    (rpos.y > o.boundsMax.y && dir.y > 0.0f) || (rpos.y < o.boundsMin.y && dir.y < 0.0f) ||
+                    (rpos.z > o.boundsMax.z && dir.z > 0.0f) || (rpos.z < o.boundsMin.z && dir.z < 0.0f);
+  const float idist = inside ? 0.0f : (away ? -1.0f : box_entry(o.boundsMin, o.boundsMax, rpos, dir));
   if (idist >= 0.0f && idist < r.dist) {
     float3 p = rpos + o.voxelBounds;
     if (idist > 0.0f) p = dir * idist + p;
@@ -291,7 +309,7 @@ RM_DEV float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
 template <bool kCount, class Vol>
 RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Isec& r, float maxDist, int maxSteps,
                          bool smooth, bool wantSurface) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   float invS;
   const float3 delta = march_delta(o, rd, o.maxVoxelIter, invS);
   JobResult j;
@@ -332,14 +350,14 @@ RM_DEV float3 sky(const RmOpts& o, float3 d) { return lerp3(o.sky1, o.sky2, d.y 
 // renderer.cl:263-269
 RM_DEV float3 light_pos(const Scene& s, const PixelState& st, int i) {
   const uint32_t seed = f2u_wrap(st.px * 1957.0f + st.py * 2173.0f + s.time * 4763.742f);
-  return table_xyz(s, seed) * s.o.lightScatter + s.o.lightPos[i];
+  return table_xyz(s, seed) * g_opts.lightScatter + g_opts.lightPos[i];
 }
 
 RM_DEV float3 reflect3(float3 v, float3 n) { return v - n * (2.0f * dot3(v, n)); }  // :271-273
 
 // renderer.cl:275-290
 RM_DEV float3 atmosphere(const Scene& s, const PixelState& st, float3 ro, float3 rd, float distance, float3 col) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   const float fa = 1.0f - expf(distance * distance * -o.fogPow);
   col = (sky(o, rd) - col) * fa + col;
   for (int i = 0; i < o.numLights; ++i) {
@@ -374,7 +392,7 @@ RM_DEV float blinn_phong(float smooth, float3 rd, float3 ldir, float3 n) {
 // renderer.cl:327-346
 template <bool kCount, class Vol>
 RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   float ao = 1.0f, d = 0.0f;
   uint32_t seed = f2u_wrap(pos.x * 3183.75f + pos.y * 1831.42f + pos.z * 2945.87f + s.time * 2671.918f);
   for (int i = 0; i <= o.aoIter && ao > 0.01f; ++i) {
@@ -396,7 +414,7 @@ RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
 template <bool kCount, class Vol>
 RM_OL_INLINE float3 object_lighting(Scene& s, const Vol& V, const PixelState& st, float3 rd, float3 ipos, const RmMaterial& m,
                               float3 n, float3 reflectCol) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   const float ao = ambient_occlusion<kCount>(s, V, ipos, n);
   float3 diff = sky(o, n) * ao;
   float3 spec = reflectCol * ao;
@@ -428,7 +446,7 @@ RM_DEV int mat_index(int id) { return id < 0 ? 0 : (id > 3 ? 3 : id); }
 // renderer.cl:383-405
 template <bool kCount, class Vol>
 RM_DEV float3 bounce_color(Scene& s, const Vol& V, const PixelState& st, float3 ro, float3 rd, Isec& isec) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   sphere_trace<kCount>(s, V, ro, rd, isec, o.maxDist, o.maxIter, false, true);
   float3 col;
   if (isec.objectID < 0) {
@@ -443,7 +461,7 @@ RM_DEV float3 bounce_color(Scene& s, const Vol& V, const PixelState& st, float3 
 // renderer.cl:407-446
 template <bool kCount, class Vol>
 RM_DEV float3 scene_color(Scene& s, const Vol& V, const PixelState& st, float3 ro, float3 rd) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   Isec isec;
   sphere_trace<kCount>(s, V, ro, rd, isec, o.maxDist, o.maxIter, true, true);
   float3 col;
@@ -475,7 +493,7 @@ RM_DEV float3 scene_color(Scene& s, const Vol& V, const PixelState& st, float3 r
 
 // renderer.cl:467-476 + :456-465
 RM_DEV float3 setup_pixel(const Scene& s, int id, PixelState& st) {
-  const RmOpts& o = s.o;
+  const RmOpts& o = g_opts;
   const float4 a = table_at(s, (uint32_t)(id * 17) + f2u_wrap(s.time * 3141.3862f));
   st.mcNormal = unit3(table_xyz(s, (uint32_t)(id * 37) + f2u_wrap(s.time * 1859.1467f)));
   st.px = (float)(id % o.width) + a.z;
@@ -494,7 +512,7 @@ template <bool kCount, class Vol>
 RM_DEV float3 render_pixel_sample(Scene& s, const Vol& V, int id) {
   PixelState st;
   const float3 rd = setup_pixel(s, id, st);
-  return scene_color<kCount>(s, V, st, st.eye, rd) * s.o.exposure;
+  return scene_color<kCount>(s, V, st, st.eye, rd) * g_opts.exposure;
 }
 
 }  // namespace plain

@@ -55,6 +55,7 @@ struct RmAccel {
   int bx, by, bz;             // brick grid extents = ceil(res / 4)
   int mx, my, mz;             // macro-cell grid extents = ceil(res / cell)
   int cell_shift;             // macro-cell edge = 1 << cell_shift voxels (>= 2)
+  float cellf;                // (float)(1 << cell_shift)
 };
 
 struct RmAccelStorage {  // owner of the device arrays behind an RmAccel view
