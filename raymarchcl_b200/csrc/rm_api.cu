@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -57,6 +58,7 @@ struct rm_ctx {
   float4* d_colour = nullptr;       // per-pass colours of one fused launch
   size_t colour_capacity = 0;       // float4 elements
   int num_sms = 0;
+  cudaEvent_t launch_done = nullptr;  // completion of this context's last render launch (DeviceGuard)
   unsigned long long* d_queue = nullptr;  // work queue head of the warp kernel
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
@@ -184,6 +186,40 @@ void resolve_timers(rm_ctx* c) {
   c->pending.clear();
 }
 
+// The render kernels read their per-launch constants from __constant__ memory (one symbol per
+// device). Launches from one stream are ordered by the stream; launches from DIFFERENT streams
+// on the same device (two contexts, or a context whose stream was swapped) are ordered here:
+// the newcomer's stream first waits for the previous launch to finish.
+struct DeviceGuard {
+  std::mutex mu;
+  rm_ctx* owner = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+DeviceGuard g_guards[64];
+
+void guard_before_launch(rm_ctx* c) {
+  DeviceGuard& g = g_guards[c->device & 63];
+  g.mu.lock();
+  if (g.owner && g.done && g.stream != c->stream) cudaStreamWaitEvent(c->stream, g.done, 0);
+}
+
+void guard_after_launch(rm_ctx* c) {
+  DeviceGuard& g = g_guards[c->device & 63];
+  if (!c->launch_done) cudaEventCreateWithFlags(&c->launch_done, cudaEventDisableTiming);
+  if (c->launch_done) cudaEventRecord(c->launch_done, c->stream);
+  g.owner = c;
+  g.stream = c->stream;
+  g.done = c->launch_done;
+  g.mu.unlock();
+}
+
+void guard_forget(rm_ctx* c) {
+  DeviceGuard& g = g_guards[c->device & 63];
+  std::lock_guard<std::mutex> lock(g.mu);
+  if (g.owner == c) { g.owner = nullptr; g.done = nullptr; g.stream = nullptr; }
+}
+
 int auto_cell_shift(int rx, int ry, int rz) {
   int m = rx > ry ? rx : ry;
   m = m > rz ? m : rz;
@@ -216,7 +252,9 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
   if (c->kernel_kind == 1) {
     for (int i = 0; i < n; ++i) {
       EventPair t = begin_timed(c, 0);
+      guard_before_launch(c);
       cudaError_t e = rm_launch_render_plain(c->d_vox, d_tables + i * tstride, passes[i], c->shard, c->d_accum, cnt, c->stream);
+      guard_after_launch(c);
       end_timed(c, t);
       if (e != cudaSuccess) return cuda_fail(c, e, "render kernel launch");
       c->stats.kernel_launches += 1;
@@ -243,6 +281,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
       for (int k = 0; k < m; ++k) { times[k] = passes[i + k].time; blend[k] = passes[i + k].frameBlend; }
       EventPair t = begin_timed(c, 0);
       cudaError_t e;
+      guard_before_launch(c);
       if (c->kernel_kind == 2) {
         const int variant = cnt ? 1 : 0;
         if (!c->warp_blocks[variant]) c->warp_blocks[variant] = rm_warp_blocks_per_sm(variant);
@@ -256,6 +295,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
         e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
                                   c->d_colour, c->d_accum, cnt, c->stream);
       }
+      guard_after_launch(c);
       end_timed(c, t);
       if (e != cudaSuccess) return cuda_fail(c, e, "render kernel launch");
       c->stats.kernel_launches += m > 1 ? 2 : 1;
@@ -347,6 +387,8 @@ void rm_destroy(rm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  guard_forget(c);
+  if (c->launch_done) cudaEventDestroy(c->launch_done);
   resolve_timers(c);
   for (EventPair& p : c->free_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_tables); cudaFree(c->d_counters);

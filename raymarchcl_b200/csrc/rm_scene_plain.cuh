@@ -25,8 +25,8 @@ namespace plain {
 // than in kernel parameters, because the shared, NON-inlined distanceToScene below can then read
 // them as constant-bank operands; through a reference to a kernel parameter it had to re-load
 // them with generic loads on every march iteration (the register budget leaves no room to keep
-// them). Consequence: two contexts must not render concurrently on the SAME device from
-// different streams (documented in include/raymarch_b200.h, Threading).
+// them). Launches that come from different streams on the same device are serialised by
+// rm_api.cu (DeviceGuard), so a later upload can never overtake a running kernel.
 static __constant__ RmOpts g_opts;
 static __constant__ RmAccel g_accel;
 
@@ -304,7 +304,7 @@ RM_DEV float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
 
 // renderer.cl:239-257
 #ifndef RM_ST_INLINE
-#define RM_ST_INLINE RM_DEV
+#define RM_ST_INLINE __device__ __noinline__  // one copy for primary / bounce / shadow traces (code size)
 #endif
 template <bool kCount, class Vol>
 RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Isec& r, float maxDist, int maxSteps,
@@ -409,7 +409,7 @@ RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
 
 // renderer.cl:348-381 (shadow :292-301 inlined)
 #ifndef RM_OL_INLINE
-#define RM_OL_INLINE RM_DEV
+#define RM_OL_INLINE __device__ __noinline__  // one copy for the primary and the bounce surfaces
 #endif
 template <bool kCount, class Vol>
 RM_OL_INLINE float3 object_lighting(Scene& s, const Vol& V, const PixelState& st, float3 rd, float3 ipos, const RmMaterial& m,

@@ -294,3 +294,46 @@ def test_production_mode_equals_counting_mode_and_oracle(gpu_renderer, oracle, k
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert np.array_equal(argb_a, argb_b)
     check_frame(b, ref_px, argb_b, oracle.tonemap(ref_px, opts[0]))
+
+
+def test_two_contexts_on_one_device_do_not_disturb_each_other(gpu_renderer):
+    """The kernels read per-launch constants from __constant__ memory; launches of different
+    contexts (different streams) on one device are ordered by the library."""
+    from raymarchcl_b200.renderer import Renderer
+    kw_a = dict(vres=64, width=128, height=72, iters=3, mat="metal")
+    kw_b = dict(vres=96, width=100, height=60, iters=2, mat="orange-stripes", theta=-45.0)
+    va, oa, ma = build_scene(**kw_a)
+    vb, ob, mb = build_scene(**kw_b)
+    gpu_renderer.set_option(2, 0)
+    ref_a, _, _ = render_gpu(gpu_renderer, va, oa, ma, 128, 72, count=False)
+    ref_b, _, _ = render_gpu(gpu_renderer, vb, ob, mb, 100, 60, count=False)
+    ra, rb = Renderer(0), Renderer(0)
+    try:
+        ra.set_volume(va); ra.clear_accum(128, 72); ra.upload_passes(oa, ma)
+        rb.set_volume(vb); rb.clear_accum(100, 60); rb.upload_passes(ob, mb)
+        for i in range(3):           # asynchronous launches, interleaved between the two contexts
+            ra.render_resident(i, 1)
+            if i < 2:
+                rb.render_resident(i, 1)
+        a, b = ra.read_accum(), rb.read_accum()
+    finally:
+        ra.close(); rb.close()
+    assert np.array_equal(a.view(np.uint32), ref_a.view(np.uint32))
+    assert np.array_equal(b.view(np.uint32), ref_b.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(vres=512, width=160, height=90, iters=1, mat="metal", volume="blob"),      # BASELINE config 3 stand-in
+    dict(vres=1024, width=96, height=54, iters=1, mat="metal2", volume="dragon"),   # BASELINE config 5 stand-in
+], ids=["c3_blob512", "c5_thin1024"])
+def test_large_volumes_match_oracle(gpu_renderer, oracle, kw):
+    """512^3 (128 MiB) and 1024^3 (1 GiB, macro-cell 16 voxels, march step 5.3 voxels) volumes."""
+    vol, opts, mcs = build_scene(**kw)
+    w, h = kw["width"], kw["height"]
+    ref_px, ref_cnt = oracle.render_frame(vol, mcs, opts, w, h)
+    gpu_renderer.set_option(2, 0)
+    px, argb, cnt = render_gpu(gpu_renderer, vol, opts, mcs, w, h)
+    assert np.array_equal(cnt, ref_cnt)
+    check_frame(px, ref_px, argb, oracle.tonemap(ref_px, opts[0]))
+    b, _, _ = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=False)
+    assert np.array_equal(px.view(np.uint32), b.view(np.uint32))
