@@ -212,7 +212,8 @@ RM_DEV bool march_counting(Scene& s, const BrickVolume& V, float3& p, float3 del
 // the position of a hit feeds the next sphere-trace step) and no fetch.
 // (Tried and measured slower, 153 vs 104 ms per C2 frame: deferring the adds until a hit needs
 // them, locating samples approximately at p + k*delta meanwhile -- the extra per-lookup work and
-// the long catch-up loops at low lane counts cost more than the adds saved on missing rays.)
+// the long catch-up loops at low lane counts cost more than the adds saved on missing rays.
+// Also without effect, 80.3 vs 79.8 ms: returning early when a long skip lands outside the grid.)
 RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
   const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
   while (rem > 0) {
@@ -222,7 +223,7 @@ RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 
     if (d != 0) {
       const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
       int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
-      n = n < rem ? n : rem;
+      if (n >= rem) return false;  // the march runs out inside space known to be empty: a miss
       rem -= n;
       // n sequential adds, binary-decomposed so that short skips (the common case) take no loop
       for (; n >= 8; n -= 8) {
