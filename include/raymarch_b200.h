@@ -46,7 +46,8 @@ typedef enum rm_status {
   RM_ERR_NO_FRAMEBUFFER = -4,/* render / tonemap / read before rm_clear_accum */
   RM_ERR_CUDA = -5,          /* a CUDA runtime call failed; see rm_last_error */
   RM_ERR_NO_DEVICE = -6,     /* no usable sm_100 device */
-  RM_ERR_UNSUPPORTED = -7
+  RM_ERR_UNSUPPORTED = -7,
+  RM_ERR_IO = -8             /* rm_load_volume_file: unreadable / malformed .vox file */
 } rm_status;
 
 /* Work and timing of the calls since the last rm_reset_stats (or rm_create).
@@ -90,6 +91,10 @@ const char* rm_last_error(const rm_ctx* ctx);
 /* ---- inputs ---- */
 /* v-buf upload (vio/load-volume, io.clj:19-33 + {:write [.. v-buf]}, core.clj:81). */
 int rm_set_volume(rm_ctx* ctx, const uint8_t* voxels, int rx, int ry, int rz);
+/* The same from a .vox file as vio/save-volume writes it (io.clj:9-17: "VOXEL", 3 x int32 big-endian,
+ * element-size byte, raw bytes): reads through pinned memory and uploads. The extents are returned
+ * through the optional out pointers (the caller needs them for TRenderOpts.voxelRes). */
+int rm_load_volume_file(rm_ctx* ctx, const char* path, int* out_rx, int* out_ry, int* out_rz);
 /* p-buf / q-buf allocation + zero fill (ops/init-buffers core.clj:140-145, {:write [p-buf ..]} :81). */
 int rm_clear_accum(rm_ctx* ctx, int width, int height);
 

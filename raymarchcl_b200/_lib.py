@@ -16,7 +16,7 @@ TABLE_FLOATS = 65536
 
 RM_OK = 0
 STATUS_NAMES = {0: "RM_OK", -1: "RM_ERR_INVALID_ARG", -2: "RM_ERR_BAD_OPTS", -3: "RM_ERR_NO_VOLUME",
-                -4: "RM_ERR_NO_FRAMEBUFFER", -5: "RM_ERR_CUDA", -6: "RM_ERR_NO_DEVICE", -7: "RM_ERR_UNSUPPORTED"}
+                -4: "RM_ERR_NO_FRAMEBUFFER", -5: "RM_ERR_CUDA", -6: "RM_ERR_NO_DEVICE", -7: "RM_ERR_UNSUPPORTED", -8: "RM_ERR_IO"}
 RM_OPT_COUNT_WORK = 1
 RM_OPT_KERNEL = 2
 RM_OPT_CELL_SHIFT = 3
@@ -25,7 +25,7 @@ RM_OPT_TRIP_LIMIT = 7
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_set_volume",
+    "rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_set_volume", "rm_load_volume_file",
     "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
     "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
     "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_shard_slots", "rm_unpack_shards", "rm_set_option", "rm_get_stats",
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     lib.rm_last_error.argtypes = [vp]
     lib.rm_last_error.restype = C.c_char_p
     lib.rm_set_volume.argtypes = [vp, vp, ip, ip, ip]
+    lib.rm_load_volume_file.argtypes = [vp, C.c_char_p, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     lib.rm_clear_accum.argtypes = [vp, ip, ip]
     lib.rm_render_pass.argtypes = [vp, vp, sz, vp, sz]
     lib.rm_render_frame.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]

@@ -422,6 +422,45 @@ int rm_set_volume(rm_ctx* c, const uint8_t* voxels, int rx, int ry, int rz) {
   return RM_OK;
 }
 
+// .vox reader: "VOXEL", 3 x int32 big-endian, 1 byte element size, raw bytes x-fastest
+// (save-volume / load-volume, io.clj:9-33).
+int rm_load_volume_file(rm_ctx* c, const char* path, int* out_rx, int* out_ry, int* out_rz) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!path) return fail(c, RM_ERR_INVALID_ARG, "rm_load_volume_file: null path");
+  std::FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(c, RM_ERR_IO, std::string("rm_load_volume_file: cannot open ") + path);
+  unsigned char head[18];
+  if (std::fread(head, 1, sizeof head, f) != sizeof head || std::memcmp(head, "VOXEL", 5) != 0) {
+    std::fclose(f);
+    return fail(c, RM_ERR_IO, std::string(path) + ": not a VOXEL file");
+  }
+  auto be32 = [&](int off) {
+    return (int)(((uint32_t)head[off] << 24) | ((uint32_t)head[off + 1] << 16) | ((uint32_t)head[off + 2] << 8) | head[off + 3]);
+  };
+  const int rx = be32(5), ry = be32(9), rz = be32(13), esize = head[17];
+  if (esize != 1 || rx <= 0 || ry <= 0 || rz <= 0 || (long long)rx * ry > 0x7fffffffLL) {
+    std::fclose(f);
+    return fail(c, RM_ERR_IO, std::string(path) + ": unsupported header (element size must be 1, extents positive)");
+  }
+  const size_t bytes = (size_t)rx * ry * rz;
+  void* host = nullptr;
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e == cudaSuccess) e = cudaMallocHost(&host, bytes);  // pinned: the upload then runs at full PCIe rate
+  if (e != cudaSuccess) { std::fclose(f); return cuda_fail(c, e, "rm_load_volume_file: pinned staging"); }
+  const size_t got = std::fread(host, 1, bytes, f);
+  std::fclose(f);
+  int rc = RM_OK;
+  if (got != bytes) rc = fail(c, RM_ERR_IO, std::string(path) + ": truncated voxel data");
+  else rc = rm_set_volume(c, static_cast<const uint8_t*>(host), rx, ry, rz);
+  cudaFreeHost(host);
+  if (rc == RM_OK) {
+    if (out_rx) *out_rx = rx;
+    if (out_ry) *out_ry = ry;
+    if (out_rz) *out_rz = rz;
+  }
+  return rc;
+}
+
 int rm_clear_accum(rm_ctx* c, int width, int height) {
   if (!c) return RM_ERR_INVALID_ARG;
   if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL / 37)

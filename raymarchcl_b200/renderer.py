@@ -14,6 +14,7 @@ CUDA library and a B200 every call raises :class:`RaymarchError` / ``ImportError
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Dict, List, Mapping, Optional, Sequence
 
 import numpy as np
@@ -78,6 +79,13 @@ class Renderer:
         rz, ry, rx = v.shape
         self._check(self._lib.rm_set_volume(self._h, v.ctypes.data, rx, ry, rz))
         self.vres = (rx, ry, rz)
+
+    def load_volume_file(self, path: str):
+        """Upload a .vox file (io.clj:19-33) straight from disk; returns (rx, ry, rz)."""
+        rx, ry, rz = C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.rm_load_volume_file(self._h, os.fsencode(path), C.byref(rx), C.byref(ry), C.byref(rz)))
+        self.vres = (rx.value, ry.value, rz.value)
+        return self.vres
 
     def clear_accum(self, width: int, height: int) -> None:
         self._check(self._lib.rm_clear_accum(self._h, int(width), int(height)))
@@ -270,3 +278,31 @@ def test_render(width: int = 640, height: int = 360, iter: int = 1, vres: int = 
         rgb = np.stack([(argb >> 16) & 255, (argb >> 8) & 255, argb & 255], axis=-1).astype(np.uint8)
         Image.fromarray(rgb, "RGB").save(out_path)
     return argb
+
+
+def test_anim(width: int, height: int, iter: int, res: int, mat: str, vname: Optional[str] = None,
+              frames: int = 35, out_dir: Optional[str] = None, device: int = 0, volume=None) -> List[np.ndarray]:
+    """``test-anim`` (core.clj:181-213): one ``init-renderer``, then per frame an orbiting camera
+    (theta 0..350 deg over ``frames`` frames, r 2.25, eye y 0.44..0.45, target y -0.15, fov 115),
+    ``update-render-option-buffer`` and a pipeline run. The volume is uploaded once and stays
+    resident (the reference's step list re-uploads it every frame, core.clj:81). Returns the ARGB
+    frames; writes ``frame-%04d.png`` into ``out_dir`` when given."""
+    args = {"width": width, "height": height, "vres": [res, res, res], "iter": iter, "mat": mat,
+            "vname": vname, "volume": volume}
+    state = init_renderer(args, device=device)
+    out: List[np.ndarray] = []
+    try:
+        for frame in range(frames):
+            t = frame / float(frames)                       # m/map-interval frame 0 35 0.0 1.0
+            frame_args = {"fov": 115.0, "targetpos": [0, -0.15, 0],
+                          "eyepos": compute_eyepos(350.0 * t, 2.25, 0.44 + 0.01 * t)}
+            update_render_option_buffer(state, frame_args)
+            argb = execute_pipeline(state, make_pipeline(state))
+            out.append(argb)
+            if out_dir:
+                from PIL import Image
+                rgb = np.stack([(argb >> 16) & 255, (argb >> 8) & 255, argb & 255], axis=-1).astype(np.uint8)
+                Image.fromarray(rgb, "RGB").save(os.path.join(out_dir, "frame-%04d.png" % frame))
+    finally:
+        state["cl-state"].close()
+    return out

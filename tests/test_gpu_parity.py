@@ -337,3 +337,43 @@ def test_large_volumes_match_oracle(gpu_renderer, oracle, kw):
     check_frame(px, ref_px, argb, oracle.tonemap(ref_px, opts[0]))
     b, _, _ = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=False)
     assert np.array_equal(px.view(np.uint32), b.view(np.uint32))
+
+
+def test_vox_file_upload_and_error_codes(gpu_renderer, tmp_path):
+    """rm_load_volume_file reads the reference's .vox format (io.clj:9-33) natively."""
+    from raymarchcl_b200 import save_volume
+    from raymarchcl_b200._lib import RaymarchError
+    kw = dict(vres=48, width=64, height=40, iters=1, mat="metal")
+    vol, opts, mcs = build_scene(**kw)
+    gpu_renderer.set_option(2, 0)
+    ref, _, _ = render_gpu(gpu_renderer, vol, opts, mcs, 64, 40, count=False)
+    path = str(tmp_path / "v.vox")
+    save_volume(path, vol)
+    assert gpu_renderer.load_volume_file(path) == (48, 48, 48)
+    gpu_renderer.clear_accum(64, 40)
+    gpu_renderer.render_frame(opts, mcs)
+    assert np.array_equal(gpu_renderer.read_accum().view(np.uint32), ref.view(np.uint32))
+    bad = tmp_path / "bad.vox"
+    bad.write_bytes(b"VOXEL" + b"\x00\x00\x00\x08" * 3 + b"\x01" + b"\x00" * 100)  # 8^3 declared, 100 bytes present
+    for p in (str(bad), str(tmp_path / "missing.vox")):
+        with pytest.raises(RaymarchError) as e:
+            gpu_renderer.load_volume_file(p)
+        assert e.value.code == -8
+    gpu_renderer.set_volume(vol)
+
+
+def test_anim_frames_equal_independent_renders(gpu_renderer):
+    """test-anim (core.clj:181-213): the volume stays resident across frames, only the opts change."""
+    import raymarchcl_b200.renderer as R
+    from raymarchcl_b200 import compute_eyepos, generate_scatter_offsets, make_gyroid_volume, make_render_option_buffers
+    vol = make_gyroid_volume(64)
+    frames = R.test_anim(96, 54, 2, 64, "metal", frames=3, volume=vol)
+    assert len(frames) == 3 and not np.array_equal(frames[0], frames[1])
+    for f, got in enumerate(frames):
+        t = f / 3.0
+        args = dict(width=96, height=54, vres=[64, 64, 64], iter=2, mat="metal", fov=115.0, targetpos=[0, -0.15, 0],
+                    eyepos=compute_eyepos(350.0 * t, 2.25, 0.44 + 0.01 * t))
+        opts = make_render_option_buffers(2, args, t_step=0.3333)
+        mcs = [generate_scatter_offsets(0x4000, 1000 + i) for i in range(2)]
+        _, argb, _ = render_gpu(gpu_renderer, vol, opts, mcs, 96, 54, count=False)
+        assert np.array_equal(argb, got)
