@@ -365,8 +365,9 @@ def run_b200(args):
             "algorithmic_bytes_per_frame": steps_frame + taps_frame,
             "kernel_ms_per_frame": kernel_s_per_frame * 1e3,
             "kernel_share_of_step": kernel_s_per_frame * 1e3 / ms_per_step,
-            "note": "1 B per reference-equivalent voxel fetch (inner steps + occupancy taps); the 16 MiB "
-                    "volume is L2-resident, so DRAM traffic is far below the algorithmic bytes by design"}
+            "note": "1 B per reference-equivalent voxel fetch (inner steps + occupancy taps). The volume and its "
+                    "derived tables are L1/L2-resident and most fetches are elided, so DRAM traffic stays far below "
+                    "the algorithmic bytes by design; the kernel is instruction-issue bound (DESIGN.md 4-5)"}
 
     line = {
         "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world,

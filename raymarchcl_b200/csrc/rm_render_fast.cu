@@ -118,6 +118,16 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
   const long long total = (long long)passes * shard.slots;
   const long long blocks = (total + kFastBlock - 1) / kFastBlock;
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+#ifndef RM_NO_CARVEOUT
+  // no shared memory is used: give the whole 256 KB of the SM's unified cache to L1 (the distance
+  // map, the bit-bricks and the spill slots all live there)
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    cudaFuncSetAttribute(k_render_bricks<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_render_bricks<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    carveout_set = true;
+  }
+#endif
   cudaError_t e = cudaMemcpyToSymbolAsync(plain::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbolAsync(plain::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
