@@ -1,3 +1,5 @@
+"""Debug helper: render one small scene through a chosen kernel (KERNEL=0|1|2, TRIPS = watchdog
+limit of kernel 2) and compare with the oracle. usage: dbg_case.py VRES WIDTH HEIGHT PASSES"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -1,4 +1,4 @@
-// Probe: do full-mask votes inside a persistent loop see all 32 lanes after divergent work?
+// Probe (kept as evidence for DESIGN.md 6): do full-mask votes inside a persistent loop see all 32 lanes after divergent work? (yes: 0 partial ballots on B200)
 #include <cstdio>
 #include <cuda_runtime.h>
 
