@@ -114,6 +114,7 @@ int rm_read_accum(rm_ctx* ctx, float* rgba_out);
 /* Store the per-pass opts blobs and tables on the device once (test-anim keeps them across frames,
  * core.clj:189-208) ... */
 int rm_upload_passes(rm_ctx* ctx, const void* const* opts, const float* const* mc, int iter);
+/* (mc == NULL: use the tables produced in place by rm_generate_scatter_tables.) */
 /* ... then render passes [first, first+count) from the resident copies; no host traffic. */
 int rm_render_resident(rm_ctx* ctx, int first, int count);
 /* Tonemap into device memory the caller owns (e.g. a torch tensor used for the NCCL gather);
@@ -125,6 +126,16 @@ int rm_sync(rm_ctx* ctx);
 /* Issue all further work of this context on a CUDA stream the caller owns (a cudaStream_t passed
  * as void*; NULL restores the context's own stream), so that the caller's events time it. */
 int rm_set_stream(rm_ctx* ctx, void* cuda_stream);
+
+/* ---- inputs generated on the device (the reference builds them on the JVM and uploads them) ---- */
+/* gen/make-gyroid-volume (generators.clj:27-42) straight into the context's volume; byte-identical
+ * to the host generator raymarchcl_b200/generators.py:make_gyroid_volume. Replaces rm_set_volume. */
+int rm_generate_gyroid_volume(rm_ctx* ctx, int rx, int ry, int rz);
+/* gen/generate-scatter-offsets (generators.clj:8-16) for java.util.Random seeds seed0 .. seed0+count-1
+ * (the reference seeds from nanoTime) into the resident table slots 0 .. count-1. */
+int rm_generate_scatter_tables(rm_ctx* ctx, int64_t seed0, int count);
+/* Parity hook: copy the resident volume (rx*ry*rz bytes) to the host. */
+int rm_read_volume(rm_ctx* ctx, uint8_t* voxels_out);
 
 /* ---- multi-GPU: interleaved tile ownership ---- */
 /* This context renders only tiles t with t % world == rank, tiles being tile_w x tile_h pixel

@@ -45,6 +45,7 @@ struct rm_ctx {
   int table_capacity = 0;
   std::vector<RmOpts> passes;  // decoded resident opts
   int resident = 0;            // passes uploaded by rm_upload_passes
+  int generated_tables = 0;    // tables produced in place by rm_generate_scatter_tables
 
   RmShard shard{};
   int shard_rank = 0, shard_world = 1, shard_tw = 32, shard_th = 32;
@@ -357,7 +358,7 @@ int rm_create(int device_id, rm_ctx** out_ctx) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
   if (prop.major != 10) {
-    char msg[160];
+    char msg[400];
     std::snprintf(msg, sizeof msg, "device %d (%s) is sm_%d%d; this library carries sm_100a code only",
                   device_id, prop.name, prop.major, prop.minor);
     return fail(nullptr, RM_ERR_NO_DEVICE, msg);
@@ -461,6 +462,62 @@ int rm_load_volume_file(rm_ctx* c, const char* path, int* out_rx, int* out_ry, i
   return rc;
 }
 
+// make-gyroid-volume on the device (generators.clj:27-42); replaces rm_set_volume for that volume.
+int rm_generate_gyroid_volume(rm_ctx* c, int rx, int ry, int rz) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (rx <= 0 || ry <= 0 || rz <= 0 || (long long)rx * ry > 0x7fffffffLL)
+    return fail(c, RM_ERR_INVALID_ARG, "rm_generate_gyroid_volume: bad extents");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)rx * ry * rz;
+  if (bytes / 64 > 0x7fffffffULL) return fail(c, RM_ERR_INVALID_ARG, "rm_generate_gyroid_volume: more than 2^37 voxels");
+  if (bytes > c->vox_capacity) {
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
+    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
+    c->vox_capacity = bytes;
+  }
+  double* d_trig = nullptr;
+  RM_CUDA(c, cudaMalloc(&d_trig, sizeof(double) * 2 * ((size_t)rx + ry + rz)));
+  cudaError_t e = rm_launch_gyroid(rx, ry, rz, d_trig, c->d_vox, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_trig);
+  if (e != cudaSuccess) return cuda_fail(c, e, "gyroid generator");
+  c->stats.kernel_launches += 4;
+  c->rx = rx; c->ry = ry; c->rz = rz;
+  c->accel.valid = false;
+  return RM_OK;
+}
+
+// Parity hook: read the resident volume back.
+int rm_read_volume(rm_ctx* c, uint8_t* voxels_out) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!voxels_out) return fail(c, RM_ERR_INVALID_ARG, "rm_read_volume: null output");
+  if (!c->d_vox) return fail(c, RM_ERR_NO_VOLUME, "no volume uploaded (rm_set_volume)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->rx * c->ry * c->rz;
+  RM_CUDA(c, cudaMemcpyAsync(voxels_out, c->d_vox, bytes, cudaMemcpyDeviceToHost, c->stream));
+  RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stats.d2h_bytes += bytes;
+  return RM_OK;
+}
+
+// generate-scatter-offsets on the device for seeds seed0 .. seed0+count-1 into the resident table
+// slots 0 .. count-1; rm_upload_passes(ctx, opts, NULL, iter) then uses them.
+int rm_generate_scatter_tables(rm_ctx* c, int64_t seed0, int count) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (count <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_generate_scatter_tables: count <= 0");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  if (c->table_capacity < count) RM_CUDA(c, cudaStreamSynchronize(c->stream));
+  int rc = ensure_tables(c, count);
+  if (rc) return rc;
+  cudaError_t e = rm_launch_scatter_tables((long long)seed0, count, c->d_tables, c->stream);
+  if (e != cudaSuccess) return cuda_fail(c, e, "scatter table generator");
+  c->stats.kernel_launches += 1;
+  c->generated_tables = count;
+  c->resident = 0;
+  return RM_OK;
+}
+
 int rm_clear_accum(rm_ctx* c, int width, int height) {
   if (!c) return RM_ERR_INVALID_ARG;
   if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL / 37)
@@ -521,24 +578,30 @@ int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, 
 
 int rm_upload_passes(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
   if (!c) return RM_ERR_INVALID_ARG;
-  if (!opts || !mc || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: null arrays or iter <= 0");
+  if (!opts || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: null opts array or iter <= 0");
+  if (!mc && iter > c->generated_tables)
+    return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: mc == NULL needs rm_generate_scatter_tables(count >= iter) first");
   int rc = require_ready(c);
   if (rc) return rc;
   RM_CUDA(c, cudaSetDevice(c->device));
   std::vector<RmOpts> dec((size_t)iter);
   for (int i = 0; i < iter; ++i) {
-    if (!opts[i] || !mc[i]) return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: null per-pass pointer");
+    if (!opts[i] || (mc && !mc[i])) return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: null per-pass pointer");
     std::memset(&dec[i], 0, sizeof(RmOpts));
     decode_opts(opts[i], &dec[i]);
     if ((rc = check_opts(c, dec[i]))) return rc;
   }
   const size_t tbytes = (size_t)RM_TABLE_FLOATS * sizeof(float);
-  if ((rc = ensure_tables(c, iter))) return rc;
-  RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < iter; ++i)
-    RM_CUDA(c, cudaMemcpyAsync(c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4), mc[i], tbytes, cudaMemcpyHostToDevice, c->stream));
-  RM_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->stats.h2d_bytes += (tbytes + RM_OPTS_BYTES) * iter;
+  if (mc) {
+    if ((rc = ensure_tables(c, iter))) return rc;
+    c->generated_tables = 0;
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < iter; ++i)
+      RM_CUDA(c, cudaMemcpyAsync(c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4), mc[i], tbytes, cudaMemcpyHostToDevice, c->stream));
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += tbytes * iter;
+  }
+  c->stats.h2d_bytes += (size_t)RM_OPTS_BYTES * iter;
   c->passes = dec;
   c->resident = iter;
   return RM_OK;

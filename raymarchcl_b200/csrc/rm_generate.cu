@@ -1,0 +1,110 @@
+// rm_generate.cu -- input generators on the device: the reference builds its test
+// volume and its per-pass random tables on the JVM and uploads them every frame
+// (generators.clj:8-42, core.clj:81,84,137-138). Generating them where they are used removes the
+// host work (the 1024^3 gyroid takes tens of seconds on one CPU core) and the PCIe upload.
+// Both generators follow the host mirror raymarchcl_b200/generators.py operation for operation in
+// fp64 (this library is compiled -fmad=false; fp64 sqrt and division are IEEE), and the tests
+// compare them with it byte for byte.
+#include "rm_kernels.h"
+
+namespace {
+
+// cos / sin of coord*scl + offset for every coordinate of one axis
+__global__ void k_axis_trig(int n, double scl, double offset, double* __restrict__ c, double* __restrict__ s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = (double)i * scl + offset;
+  c[i] = cos(a);
+  s[i] = sin(a);
+}
+
+// make-gyroid-volume (generators.clj:27-42): g = |cos x sin z + cos y sin x + cos z sin y| - 1 in
+// the slabs (z & 63) >= 32; |0.2 - g| < 0.05 -> 64 / 128 by x stripe; else g > 0.35 -> 255.
+// One thread per 4 voxels of a row (one 32-bit store).
+__global__ void __launch_bounds__(256)
+k_gyroid(int rx, int ry, int rz, const double* __restrict__ cx, const double* __restrict__ sx,
+         const double* __restrict__ cy, const double* __restrict__ sy, const double* __restrict__ cz,
+         const double* __restrict__ sz, uint8_t* __restrict__ vox) {
+  const int qx = (rx + 3) >> 2;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)qx * ry * rz) return;
+  const int x0 = (int)(t % qx) * 4;
+  const int y = (int)((t / qx) % ry);
+  const int z = (int)(t / ((long long)qx * ry));
+  uint8_t out[4] = {0, 0, 0, 0};
+  if ((z & 63) >= 32) {
+    const double cyv = cy[y], syv = sy[y], czv = cz[z], szv = sz[z];
+    for (int k = 0; k < 4; ++k) {
+      const int x = x0 + k;
+      if (x >= rx) break;
+      const double g = fabs(cx[x] * szv + cyv * sx[x] + czv * syv) - 1.0;
+      if (fabs(0.2 - g) < 0.05) out[k] = (x & 63) < 32 ? 64 : 128;
+      else if (g > 0.35) out[k] = 255;
+    }
+  }
+  uint8_t* row = vox + ((size_t)z * ry + y) * rx + x0;
+  if (x0 + 3 < rx && (((uintptr_t)row) & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(row) = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+  } else {
+    for (int k = 0; k < 4 && x0 + k < rx; ++k) row[k] = out[k];
+  }
+}
+
+// java.util.Random: state' = (state * 0x5DEECE66D + 0xB) mod 2^48; k steps at once by squaring
+__device__ unsigned long long lcg_jump(unsigned long long s, unsigned long long k) {
+  const unsigned long long M = (1ull << 48) - 1;
+  unsigned long long a = 0x5DEECE66Dull, c = 0xBull;  // one step: s -> a*s + c
+  while (k) {
+    if (k & 1) s = (a * s + c) & M;
+    c = (a * c + c) & M;  // two steps: a*(a*s + c) + c
+    a = (a * a) & M;
+    k >>= 1;
+  }
+  return s;
+}
+
+// generate-scatter-offsets (generators.clj:8-16) with an explicit seed: entry i of table t takes
+// nextDouble() number 4i..4i+3 of java.util.Random(seed0 + t); each component is
+// float(2*d - 1), the vector is scaled by 1/sqrt(sum of squares) in double and stored as float.
+__global__ void __launch_bounds__(256)
+k_scatter_tables(long long seed0, int tables, float4* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;  // entry within a table
+  const int t = blockIdx.y;
+  if (i > RM_TABLE_MASK || t >= tables) return;
+  const unsigned long long M = (1ull << 48) - 1;
+  unsigned long long s = ((unsigned long long)(seed0 + t) ^ 0x5DEECE66Dull) & M;
+  s = lcg_jump(s, 8ull * (unsigned long long)i);  // two next() calls per double, four doubles per entry
+  double v[4];
+  for (int k = 0; k < 4; ++k) {
+    s = (s * 0x5DEECE66Dull + 0xBull) & M;
+    const long long hi = (long long)(s >> (48 - 26));
+    s = (s * 0x5DEECE66Dull + 0xBull) & M;
+    const long long lo = (long long)(s >> (48 - 27));
+    const double d = (double)((hi << 27) + lo) * (1.0 / 9007199254740992.0);
+    v[k] = (double)(float)(2.0 * d - 1.0);
+  }
+  const double m = 1.0 / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+  out[(size_t)t * (RM_TABLE_MASK + 1) + i] =
+      make_float4((float)(v[0] * m), (float)(v[1] * m), (float)(v[2] * m), (float)(v[3] * m));
+}
+
+}  // namespace
+
+cudaError_t rm_launch_gyroid(int rx, int ry, int rz, double* d_trig, uint8_t* d_vox, cudaStream_t stream) {
+  // d_trig: 2 * (rx + ry + rz) doubles of scratch
+  const double scl = 0.01 * (512.0 / (double)rx);
+  double *cx = d_trig, *sx = cx + rx, *cy = sx + rx, *sy = cy + ry, *cz = sy + ry, *sz = cz + rz;
+  k_axis_trig<<<(rx + 127) / 128, 128, 0, stream>>>(rx, scl, 0.3875, cx, sx);
+  k_axis_trig<<<(ry + 127) / 128, 128, 0, stream>>>(ry, scl, 0.0, cy, sy);
+  k_axis_trig<<<(rz + 127) / 128, 128, 0, stream>>>(rz, scl, 0.0, cz, sz);
+  const long long n = (long long)((rx + 3) >> 2) * ry * rz;
+  k_gyroid<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rx, ry, rz, cx, sx, cy, sy, cz, sz, d_vox);
+  return cudaGetLastError();
+}
+
+cudaError_t rm_launch_scatter_tables(long long seed0, int tables, float4* d_tables, cudaStream_t stream) {
+  if (tables <= 0) return cudaSuccess;
+  const dim3 grid((RM_TABLE_MASK + 1 + 255) / 256, (unsigned)tables);
+  k_scatter_tables<<<grid, 256, 0, stream>>>(seed0, tables, d_tables);
+  return cudaGetLastError();
+}

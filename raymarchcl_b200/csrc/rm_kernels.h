@@ -70,3 +70,9 @@ cudaError_t rm_launch_render_warp(const RmOpts& opts, const RmShard& shard, cons
                                   const float4* d_tables, const float* times, int passes, float4* d_colour,
                                   float4* d_accum, unsigned long long* d_queue, RmCounters* d_counters,
                                   unsigned* d_watchdog, unsigned trip_limit, int grid_blocks, cudaStream_t stream);
+
+// ---- device-side input generators (rm_generate.cu) ----
+// make-gyroid-volume (generators.clj:27-42) into d_vox (rx*ry*rz bytes); d_trig = 2*(rx+ry+rz) doubles of scratch.
+cudaError_t rm_launch_gyroid(int rx, int ry, int rz, double* d_trig, uint8_t* d_vox, cudaStream_t stream);
+// generate-scatter-offsets (generators.clj:8-16) for java.util.Random seeds seed0 .. seed0+tables-1.
+cudaError_t rm_launch_scatter_tables(long long seed0, int tables, float4* d_tables, cudaStream_t stream);

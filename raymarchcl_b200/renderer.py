@@ -87,6 +87,22 @@ class Renderer:
         self.vres = (rx.value, ry.value, rz.value)
         return self.vres
 
+    def generate_gyroid_volume(self, vres) -> None:
+        """``make-gyroid-volume`` (generators.clj:27-42) on the device instead of host + upload."""
+        rx, ry, rz = [int(vres)] * 3 if isinstance(vres, (int, np.integer)) else [int(v) for v in vres]
+        self._check(self._lib.rm_generate_gyroid_volume(self._h, rx, ry, rz))
+        self.vres = (rx, ry, rz)
+
+    def generate_scatter_tables(self, seed0: int, count: int) -> None:
+        """``generate-scatter-offsets`` for seeds seed0..seed0+count-1 into the resident table slots."""
+        self._check(self._lib.rm_generate_scatter_tables(self._h, int(seed0), int(count)))
+
+    def read_volume(self) -> np.ndarray:
+        rx, ry, rz = self.vres
+        out = np.empty((rz, ry, rx), dtype=np.uint8)
+        self._check(self._lib.rm_read_volume(self._h, out.ctypes.data))
+        return out
+
     def clear_accum(self, width: int, height: int) -> None:
         self._check(self._lib.rm_clear_accum(self._h, int(width), int(height)))
         self.width, self.height = int(width), int(height)
@@ -113,7 +129,14 @@ class Renderer:
         n, oarr, marr, keep = self._ptr_arrays(opts, mcs)
         self._check(self._lib.rm_render_frame(self._h, oarr, marr, n))
 
-    def upload_passes(self, opts: Sequence[bytes], mcs: Sequence[np.ndarray]) -> None:
+    def upload_passes(self, opts: Sequence[bytes], mcs: Optional[Sequence[np.ndarray]]) -> None:
+        """``mcs=None``: use the tables made in place by :meth:`generate_scatter_tables`."""
+        if mcs is None:
+            n = len(opts)
+            obufs = [C.create_string_buffer(o, OPTS_BYTES) for o in opts]
+            oarr = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in obufs])
+            self._check(self._lib.rm_upload_passes(self._h, oarr, None, n))
+            return
         n, oarr, marr, keep = self._ptr_arrays(opts, mcs)
         self._check(self._lib.rm_upload_passes(self._h, oarr, marr, n))
 
