@@ -220,24 +220,23 @@ RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 
     const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
     if (!in_grid(o, x, y, z)) return false;
     const int d = V.cell_dist(x, y, z);
+    int n = 1;  // samples consumed by this iteration: this one plus the ones known to be empty
     if (d != 0) {
       const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
-      int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
-      if (n >= rem) return false;  // the march runs out inside space known to be empty: a miss
-      rem -= n;
-      // n sequential adds, binary-decomposed so that short skips (the common case) take no loop
-      for (; n >= 8; n -= 8) {
-        p = p + delta; p = p + delta; p = p + delta; p = p + delta;
-        p = p + delta; p = p + delta; p = p + delta; p = p + delta;
-      }
-      if (n & 4) { p = p + delta; p = p + delta; p = p + delta; p = p + delta; }
-      if (n & 2) { p = p + delta; p = p + delta; }
-      if (n & 1) p = p + delta;
-    } else {
-      if ((V.word(g_accel.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) return true;
-      p = p + delta;
-      rem -= 1;
+      if (reach > 0.0f) n = 1 + f2i_sat(fminf(reach * invS, 1e6f));
+    } else if ((V.word(g_accel.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) {
+      return true;
     }
+    if (n >= rem) return false;  // the march runs out inside space known to be empty: a miss
+    rem -= n;
+    // n sequential adds, binary-decomposed so that short skips (the common case) take no loop
+    for (; n >= 8; n -= 8) {
+      p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+      p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+    }
+    if (n & 4) { p = p + delta; p = p + delta; p = p + delta; p = p + delta; }
+    if (n & 2) { p = p + delta; p = p + delta; }
+    if (n & 1) p = p + delta;
   }
   return false;
 }
