@@ -400,8 +400,20 @@ RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
     seed += 37u;
     const float3 n = unit3(table_xyz(s, seed) * 0.2f + n0);
     float invS;
-    const float3 delta = march_delta(o, n, o.maxVoxelIter / 2, invS);
-    const JobResult h = scene_distance<kCount>(s, V, n * d + pos, n, delta, o.maxVoxelIter / 2, invS, false);
+    const int msteps = o.maxVoxelIter / 2;
+    const float3 delta = march_delta(o, n, msteps, invS);
+    // A probe changes ao only through max((d - h)*aoAmp/d, 0), which is 0 (factor exactly 1) for
+    // every h >= d when aoAmp >= 0: a voxel hit whose distance len - voxelSize is >= d, and the
+    // ground plane beyond d, are the same as no hit at all. Sample k of the march lies k world
+    // steps from the probe origin, so only the first (d + voxelSize)/step samples can matter;
+    // the production kernels march those (plus two for rounding), the counting kernels all of
+    // them like the reference (renderer.cl:342 marches maxVoxelIter/2 = 96 samples per probe).
+    int limit = msteps;
+    if (!kCount && o.aoAmp >= 0.0f && d > 0.0f) {
+      const float k = (d + o.voxelSize) * 1.01f / len3(delta * o.voxelBounds2);
+      if (k < (float)msteps) limit = f2i_sat(k) + 2 < msteps ? f2i_sat(k) + 2 : msteps;
+    }
+    const JobResult h = scene_distance<kCount>(s, V, n * d + pos, n, delta, limit, invS, false);
     ao *= 1.0f - cl_max((d - h.dist) * o.aoAmp / d, 0.0f);
   }
   return ao;
@@ -426,13 +438,23 @@ RM_OL_INLINE float3 object_lighting(Scene& s, const Vol& V, const PixelState& st
     if (att > o.minLightAtt) {
       const float3 ldir = unit3(dl);
       const float lmax = cl_min(sqrtf(ld2) - o.shadowBias, o.maxDist);
-      Isec sh;
-      sphere_trace<kCount>(s, V, ipos + ldir * o.shadowBias, ldir, sh, lmax, o.shadowIter, false, false);
-      const float sf = sh.distance < lmax ? 0.0f : 1.0f;
-      if (sf > 0.0f) {
-        const float3 inc = (o.lightColor[i] * sf) * att;
-        diff = diff + inc * cl_max(0.0f, dot3(ldir, n));
-        spec = spec + inc * blinn_phong(m.smoothness, rd, ldir, n);
+      const float kd = cl_max(0.0f, dot3(ldir, n));
+      const float ks = blinn_phong(m.smoothness, rd, ldir, n);
+      const float3 inc = (o.lightColor[i] * 1.0f) * att;  // (lightColor * shadow factor 1) * att, :369
+      // A light that faces neither the surface (kd = 0) nor its highlight (ks = 0) adds inc*0 to
+      // both sums whether or not it is shadowed, i.e. nothing as long as inc is finite: its shadow
+      // ray cannot change the result and is not traced. (The counting kernels trace it: the
+      // reference does, and its work is part of the reference-equivalent counters.)
+      const float3 zero = inc * 0.0f;
+      const bool irrelevant = !kCount && kd == 0.0f && ks == 0.0f && zero.x == 0.0f && zero.y == 0.0f && zero.z == 0.0f;
+      if (!irrelevant) {
+        Isec sh;
+        sphere_trace<kCount>(s, V, ipos + ldir * o.shadowBias, ldir, sh, lmax, o.shadowIter, false, false);
+        const float sf = sh.distance < lmax ? 0.0f : 1.0f;
+        if (sf > 0.0f) {
+          diff = diff + inc * kd;
+          spec = spec + inc * ks;
+        }
       }
     }
     diff = diff * m.albedo;
