@@ -316,13 +316,35 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
   j.g = 0.0f; j.dist = 0.0f; j.hit = false; j.closer = false; j.p = f3s(0.0f);
   r.distance = o.startDist;
   r.pos = ro;
+  // distanceToScene returns min(voxel distance, ground distance g): a voxel hit whose distance
+  // len - voxelSize is >= g returns the same pair as no hit, so only the samples within
+  // g + voxelSize of the ray position can change the returned distance; for a shadow ray
+  // (distance-only consumer, wantSurface == false) the same holds for hits beyond the light
+  // (they and "no hit" both end the trace as lit). The production kernels march only those samples
+  // (plus two for rounding). The one thing a far hit still decides is the reference's quirk that
+  // the LAST call's voxel normal wins even when the ground is closer (renderer.cl:224-228): when a
+  // surface is wanted and the last call was cut short without a hit, that call is repeated in full.
+  const float inv_step = kCount ? 0.0f : 1.01f / len3(delta * o.voxelBounds2);
+  bool cut = false;
   while (--maxSteps >= 0) {
     if (kCount) s.w.outer++;
     r.pos = ro + rd * r.distance;
-    j = scene_distance<kCount>(s, V, r.pos, rd, delta, o.maxVoxelIter, invS, smooth);
+    int limit = o.maxVoxelIter;
+    if (!kCount) {
+      float reach = r.pos.y + o.groundY;
+      // (a hit just beyond the light must also be farther than eps, or it could end the trace as
+      // "converged", i.e. shadowed, before the light is reached)
+      if (!wantSurface) reach = fminf(reach, fmaxf(maxDist - r.distance, o.eps));
+      const float k = (reach + o.voxelSize) * inv_step;
+      cut = k < (float)(limit - 2);
+      if (cut) limit = f2i_sat(k) + 2;
+    }
+    j = scene_distance<kCount>(s, V, r.pos, rd, delta, limit, invS, smooth);
     if (fabsf(j.dist) <= o.eps || r.distance >= maxDist) break;
     r.distance += j.dist;
   }
+  if (!kCount && wantSurface && cut && !j.hit)
+    j = scene_distance<kCount>(s, V, r.pos, rd, delta, o.maxVoxelIter, invS, smooth);
   const bool miss = r.distance >= maxDist;
   if (miss) {
     r.pos = ro + rd * r.distance;

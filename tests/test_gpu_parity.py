@@ -403,3 +403,24 @@ def test_device_scatter_tables_reproduce_java_random(gpu_renderer):
     r.upload_passes(opts, None)
     r.render_resident(0, 3)
     assert np.array_equal(r.read_accum().view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(vres=64, width=96, height=64, iters=2, mat="metal", groundY=0.2),                  # ground plane cuts the volume
+    dict(vres=128, width=80, height=60, iters=1, mat="metal2", groundY=-0.3, theta=60.0),   # plane at y=+0.3, camera below it
+    dict(vres=64, width=64, height=48, iters=1, mat="ao", groundY=0.0, volume="full"),
+], ids=["groundY0.2", "groundY-0.3", "full_groundY0"])
+def test_ground_plane_inside_the_volume(gpu_renderer, oracle, kw):
+    """The production kernels march only the samples that can change distanceToScene's result and
+    repeat the last call in full when the reference's 'last voxel normal wins even if the ground is
+    closer' quirk (renderer.cl:224-228) could apply. A ground plane that cuts through the voxels
+    makes that quirk the common case."""
+    vol, opts, mcs = build_scene(**kw)
+    w, h = kw["width"], kw["height"]
+    ref_px, ref_cnt = oracle.render_frame(vol, mcs, opts, w, h)
+    gpu_renderer.set_option(2, 0)
+    a, argb_a, cnt = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=True)
+    b, argb_b, _ = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=False)
+    assert np.array_equal(cnt, ref_cnt)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    check_frame(b, ref_px, argb_b, oracle.tonemap(ref_px, opts[0]))
