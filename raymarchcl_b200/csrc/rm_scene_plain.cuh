@@ -18,6 +18,16 @@
 #include "rm_math.cuh"
 #include "rm_types.h"
 
+// Statistics hooks of the host simulation (tests/hostsim): empty in the CUDA build.
+#ifndef RM_STAT_LOOKUP
+#define RM_STAT_LOOKUP() ((void)0)
+#define RM_STAT_SKIP(n) ((void)0)
+#define RM_STAT_JUMP(n) ((void)0)
+#define RM_STAT_SEQ(n) ((void)0)
+#define RM_STAT_MARCH() ((void)0)
+#define RM_STAT_TRACE() ((void)0)
+#endif
+
 namespace plain {
 
 // Per-launch constants. They live in __constant__ memory (one copy per translation unit that
@@ -215,11 +225,13 @@ RM_DEV bool march_counting(Scene& s, const BrickVolume& V, float3& p, float3 del
 // the long catch-up loops at low lane counts cost more than the adds saved on missing rays.
 // Also without effect, 80.3 vs 79.8 ms: returning early when a long skip lands outside the grid.)
 RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
+  RM_STAT_MARCH();
   const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
   while (rem > 0) {
     const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
     if (!in_grid(o, x, y, z)) return false;
     const int d = V.cell_dist(x, y, z);
+    RM_STAT_LOOKUP();
     int n = 1;  // samples consumed by this iteration: this one plus the ones known to be empty
     if (d != 0) {
       const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
@@ -229,6 +241,7 @@ RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 
     }
     if (n >= rem) return false;  // the march runs out inside space known to be empty: a miss
     rem -= n;
+    RM_STAT_SKIP(n);
     // n sequential adds, binary-decomposed so that short skips (the common case) take no loop
     for (; n >= 8; n -= 8) {
       p = p + delta; p = p + delta; p = p + delta; p = p + delta;
@@ -310,6 +323,7 @@ template <bool kCount, class Vol>
 RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Isec& r, float maxDist, int maxSteps,
                          bool smooth, bool wantSurface) {
   const RmOpts& o = g_opts;
+  RM_STAT_TRACE();
   float invS;
   const float3 delta = march_delta(o, rd, o.maxVoxelIter, invS);
   JobResult j;
