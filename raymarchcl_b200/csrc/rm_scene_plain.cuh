@@ -26,6 +26,7 @@
 #define RM_STAT_SEQ(n) ((void)0)
 #define RM_STAT_MARCH() ((void)0)
 #define RM_STAT_TRACE() ((void)0)
+#define RM_STAT_EVENT(id) ((void)0)
 #endif
 
 namespace plain {
@@ -288,11 +289,15 @@ RM_SD_INLINE JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float
                     (rpos.y > o.boundsMax.y && dir.y > 0.0f) || (rpos.y < o.boundsMin.y && dir.y < 0.0f) ||
                     (rpos.z > o.boundsMax.z && dir.z > 0.0f) || (rpos.z < o.boundsMin.z && dir.z < 0.0f);
   const float idist = inside ? 0.0f : (away ? -1.0f : box_entry(o.boundsMin, o.boundsMax, rpos, dir));
+  RM_STAT_EVENT(0);
+  RM_STAT_EVENT(inside ? 1 : (away ? 2 : 3));
   if (idist >= 0.0f && idist < r.dist) {
+    RM_STAT_EVENT(4);
     float3 p = rpos + o.voxelBounds;
     if (idist > 0.0f) p = dir * idist + p;
     p = p * o.invVoxelScale;
     if (march<kCount>(s, V, p, delta, steps, invS)) {
+      RM_STAT_EVENT(5);
       r.hit = true;
       r.p = p;
       if (kCount) {
@@ -315,6 +320,49 @@ RM_DEV float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
   return delta;
 }
 
+// A conservative window [tin, tout] of ray parameters outside of which a distanceToScene call at
+// ro + rd*d cannot reach the voxel march (production kernels only). The line is clipped against the
+// voxel box GROWN by kGrow on every side, in ordinary (not pinned) arithmetic:
+//   d > tout            the evaluation point lies beyond a slab of the true box by >= kGrow and moves
+//                       away from it: this is exactly the `away` case of scene_distance (-1, no march);
+//   tin - d > g + slack the fp32 entry distance the reference computes from that point differs from
+//                       the true one by ~1e-5 at these magnitudes (|coordinates| <= 128, see `ok`), the
+//                       true one is >= tin - d, so it is >= g: `idist < res.x` (renderer.cl:213) fails;
+//   tin = +inf          the line misses the grown box altogether: the slab test returns -1 everywhere.
+// Whenever the window cannot be trusted (huge coordinates, NaNs) it is (-inf, +inf): every call is
+// then evaluated in full. The window only selects WHICH calls are evaluated in full; a call that is
+// skipped returns the ground-plane pair, which is what the full evaluation returns without a march.
+RM_DEV void march_window(const RmOpts& o, float3 ro, float3 rd, float maxDist, float& tin, float& tout) {
+  const float kGrow = 0.01f, kTiny = 1e-5f, kBig = 64.0f, kInf = 3.0e38f;
+  tin = -kInf;
+  tout = kInf;
+  const float ro_[3] = {ro.x, ro.y, ro.z}, rd_[3] = {rd.x, rd.y, rd.z};
+  const float lo_[3] = {o.boundsMin.x, o.boundsMin.y, o.boundsMin.z}, hi_[3] = {o.boundsMax.x, o.boundsMax.y, o.boundsMax.z};
+  bool ok = maxDist <= kBig, miss = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    ok = ok && fabsf(ro_[i]) <= kBig && fabsf(lo_[i]) <= kBig && fabsf(hi_[i]) <= kBig && fabsf(rd_[i]) <= 2.0f;
+  if (!ok) return;
+  float a = -kInf, b = kInf;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float l = lo_[i] - kGrow - ro_[i], h = hi_[i] + kGrow - ro_[i];
+    if (fabsf(rd_[i]) < kTiny) {
+      // the coordinate moves by < kTiny * (kBig + a ground step) over the whole trace: outside the
+      // grown slab now means outside the true slab for good, inside means no constraint
+      if (l > 0.0f || h < 0.0f) miss = true;
+    } else {
+      const float inv = __fdividef(1.0f, rd_[i]);
+      const float t0 = l * inv, t1 = h * inv;
+      a = fmaxf(a, fminf(t0, t1));
+      b = fminf(b, fmaxf(t0, t1));
+    }
+  }
+  if (miss || b < a || b < 0.0f) { tin = kInf; tout = -kInf; return; }
+  tin = a;
+  tout = b;
+}
+
 // renderer.cl:239-257
 #ifndef RM_ST_INLINE
 #define RM_ST_INLINE __device__ __noinline__  // one copy for primary / bounce / shadow traces (code size)
@@ -324,6 +372,7 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
                          bool smooth, bool wantSurface) {
   const RmOpts& o = g_opts;
   RM_STAT_TRACE();
+  RM_STAT_EVENT(wantSurface ? 6 : 7);
   float invS;
   const float3 delta = march_delta(o, rd, o.maxVoxelIter, invS);
   JobResult j;
@@ -340,23 +389,41 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
   // surface is wanted and the last call was cut short without a hit, that call is repeated in full.
   const float inv_step = kCount ? 0.0f : 1.01f / len3(delta * o.voxelBounds2);
   bool cut = false;
+  // Most distanceToScene calls of a trace cannot reach the voxel march at all (C2: 65 of 81 per
+  // pixel-sample -- the ray has left the box, has not come within the ground distance of it, or
+  // never meets it): they return the ground-plane pair, and the production kernels evaluate just
+  // that (march_window says which calls those are). The counting kernels evaluate every call in full.
+  float tin = -3.0e38f, tout = 3.0e38f;
+  if (!kCount) march_window(o, ro, rd, maxDist, tin, tout);
   while (--maxSteps >= 0) {
     if (kCount) s.w.outer++;
+    RM_STAT_EVENT(wantSurface ? 8 : 9);
     r.pos = ro + rd * r.distance;
-    int limit = o.maxVoxelIter;
-    if (!kCount) {
-      float reach = r.pos.y + o.groundY;
-      // (a hit just beyond the light must also be farther than eps, or it could end the trace as
-      // "converged", i.e. shadowed, before the light is reached)
-      if (!wantSurface) reach = fminf(reach, fmaxf(maxDist - r.distance, o.eps));
-      const float k = (reach + o.voxelSize) * inv_step;
-      cut = k < (float)(limit - 2);
-      if (cut) limit = f2i_sat(k) + 2;
+    const float g = r.pos.y + o.groundY;
+    if (!kCount && (r.distance > tout || tin - r.distance > g * 1.0001f + 1e-3f || g <= 0.0f)) {
+      RM_STAT_EVENT(12);
+      j.g = g;
+      j.dist = g < 1e5f ? g : 1e5f;
+      j.hit = false;
+      j.closer = false;
+      cut = false;
+    } else {
+      int limit = o.maxVoxelIter;
+      if (!kCount) {
+        float reach = g;
+        // (a hit just beyond the light must also be farther than eps, or it could end the trace as
+        // "converged", i.e. shadowed, before the light is reached)
+        if (!wantSurface) reach = fminf(reach, fmaxf(maxDist - r.distance, o.eps));
+        const float k = (reach + o.voxelSize) * inv_step;
+        cut = k < (float)(limit - 2);
+        if (cut) limit = f2i_sat(k) + 2;
+      }
+      j = scene_distance<kCount>(s, V, r.pos, rd, delta, limit, invS, smooth);
     }
-    j = scene_distance<kCount>(s, V, r.pos, rd, delta, limit, invS, smooth);
     if (fabsf(j.dist) <= o.eps || r.distance >= maxDist) break;
     r.distance += j.dist;
   }
+  if (!kCount && wantSurface && cut && !j.hit) RM_STAT_EVENT(10);
   if (!kCount && wantSurface && cut && !j.hit)
     j = scene_distance<kCount>(s, V, r.pos, rd, delta, o.maxVoxelIter, invS, smooth);
   const bool miss = r.distance >= maxDist;
@@ -449,6 +516,7 @@ RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
       const float k = (d + o.voxelSize) * 1.01f / len3(delta * o.voxelBounds2);
       if (k < (float)msteps) limit = f2i_sat(k) + 2 < msteps ? f2i_sat(k) + 2 : msteps;
     }
+    RM_STAT_EVENT(11);
     const JobResult h = scene_distance<kCount>(s, V, n * d + pos, n, delta, limit, invS, false);
     ao *= 1.0f - cl_max((d - h.dist) * o.aoAmp / d, 0.0f);
   }

@@ -15,7 +15,7 @@
 
 // statistics hooks of the production march (empty in the CUDA build)
 struct SimStats {
-  unsigned long long lookups, skips, skipped_samples, jumps, jump_samples, seq_adds, marches, traces, hist[16];
+  unsigned long long lookups, skips, skipped_samples, jumps, jump_samples, seq_adds, marches, traces, hist[16], events[32];
 };
 static thread_local SimStats t_stats;
 #define RM_STAT_LOOKUP() (t_stats.lookups++)
@@ -24,6 +24,7 @@ static thread_local SimStats t_stats;
 #define RM_STAT_SEQ(n) (t_stats.seq_adds += (n))
 #define RM_STAT_MARCH() (t_stats.marches++)
 #define RM_STAT_TRACE() (t_stats.traces++)
+#define RM_STAT_EVENT(id) (t_stats.events[(id)]++)
 static inline int stat_bucket(int n) {
   int b = 0;
   while (n > 1 && b < 15) { n >>= 1; ++b; }

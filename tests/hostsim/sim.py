@@ -47,5 +47,7 @@ class HostSim:
         out = np.zeros(n, dtype=np.uint64)
         self.lib.sim_get_stats(out, int(reset))
         d = {k: int(out[i]) for i, k in enumerate(STAT_NAMES)}
-        d["skip_hist_log2"] = [int(x) for x in out[len(STAT_NAMES):]]
+        k = len(STAT_NAMES)
+        d["skip_hist_log2"] = [int(x) for x in out[k:k + 16]]
+        d["events"] = [int(x) for x in out[k + 16:k + 48]]
         return d
