@@ -117,6 +117,7 @@ cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso
   a.cell_shift = cell_shift < 2 ? 2 : cell_shift;
   const int cell = 1 << a.cell_shift;
   a.cellf = (float)cell;
+  a.rxf = (float)rx; a.ryf = (float)ry; a.rzf = (float)rz;
   a.mx = (rx + cell - 1) >> a.cell_shift; a.my = (ry + cell - 1) >> a.cell_shift; a.mz = (rz + cell - 1) >> a.cell_shift;
   const size_t nb = (size_t)a.bx * a.by * a.bz, nc = (size_t)a.mx * a.my * a.mz;
   cudaError_t e;

@@ -16,7 +16,7 @@
 namespace {
 
 #ifndef RM_FAST_BLOCK
-#define RM_FAST_BLOCK 128
+#define RM_FAST_BLOCK 256  // measured on B200 (C2): 64 / 128 / 256 / 512 threads at 40 warps per SM: 42.4 / 42.3 / 40.8 / 42.4 ms
 #endif
 constexpr int kFastBlock = RM_FAST_BLOCK;
 
@@ -29,11 +29,12 @@ struct FastParams {
   int passes;
 };
 
-// 10 resident blocks of 128 threads per SM (48 registers per thread, a few spills to L1): the
-// kernel is latency- and issue-bound, not register-bound; measured on B200 (C2) 1 -> 6 -> 8 -> 10 -> 12
-// blocks: 178 -> 140 -> 124 -> 118 -> 116 ms per frame.
+// 40 resident warps per SM (48 registers per thread, a few spills to L1): the kernel is latency-
+// and issue-bound, not register-bound; measured on B200 (C2) with 128-thread blocks, 1 -> 6 -> 8 ->
+// 10 -> 12 blocks: 178 -> 140 -> 124 -> 118 -> 116 ms per frame (early kernel); re-measured on the
+// current one: 32 / 40 / 48 warps = 43.5 / 41.9 / 42.0 ms.
 #ifndef RM_FAST_MINBLOCKS
-#define RM_FAST_MINBLOCKS 10
+#define RM_FAST_MINBLOCKS 5
 #endif
 
 template <bool kCount>

@@ -28,6 +28,11 @@
 #define RM_STAT_TRACE() ((void)0)
 #define RM_STAT_EVENT(id) ((void)0)
 #endif
+#ifndef RM_STAT_SITE
+#define RM_STAT_SITE(id) ((void)0)      // which call site of the pixel-sample the following work belongs to
+#define RM_STAT_LEVEL(l) ((void)0)     // 0 = primary surface, k = k-th bounce
+#define RM_STAT_LEVEL_GET() 0
+#endif
 
 namespace plain {
 
@@ -227,17 +232,27 @@ RM_DEV bool march_counting(Scene& s, const BrickVolume& V, float3& p, float3 del
 // Also without effect, 80.3 vs 79.8 ms: returning early when a long skip lands outside the grid.)
 RM_DEV bool march_fast(const RmOpts& o, const BrickVolume& V, float3& p, float3 delta, int rem, float invS) {
   RM_STAT_MARCH();
-  const float rxf = (float)o.rx, ryf = (float)o.ry, rzf = (float)o.rz;
+  // Conversions run on the quarter-rate XU pipe, which this loop saturates (ncu: pipe_xu the busiest
+  // pipe): only the three truncations that ARE the reference's convert_int3_sat stay on it. The
+  // grid extents come as floats from the constant bank, and the skip length is computed with
+  // magic-number adds: (float)(d-1) = as_float(0x4b000000 | (d-1)) - 2^23, and
+  // round-to-nearest(x - 0.5) <= floor(x) = as_int((x - 0.5) + 1.5*2^23) - as_int(1.5*2^23) for
+  // 0 <= x < 2^22 (a skip may be one sample shorter than the bound allows, never longer).
+  const float A = g_accel.cellf * invS, B = 0.25f * invS + 0.5f;  // invS <= 2000 (march_delta)
   while (rem > 0) {
-    const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
+    const int x = f2i_sat(p.x * g_accel.rxf), y = f2i_sat(p.y * g_accel.ryf), z = f2i_sat(p.z * g_accel.rzf);
     if (!in_grid(o, x, y, z)) return false;
     const int d = V.cell_dist(x, y, z);
     RM_STAT_LOOKUP();
+    RM_STAT_EVENT(d == 0 ? 13 : (d == 1 ? 14 : (d == 2 ? 15 : 16)));
     int n = 1;  // samples consumed by this iteration: this one plus the ones known to be empty
-    if (d != 0) {
-      const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
-      if (reach > 0.0f) n = 1 + f2i_sat(fminf(reach * invS, 1e6f));
-    } else if ((V.word(g_accel.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull) {
+    if (d > 1) {
+      // reach = (d-1)*cell - 0.25 voxels (the slack covers the rounding drift of the recurrence);
+      // n = 1 + floor(reach / largest step), conservatively
+      const float dm1 = __int_as_float(0x4b000000 | (d - 1)) - 8388608.0f;
+      const float k = (dm1 * A - B) + 12582912.0f;
+      n = 1 + (__float_as_int(k) - 0x4b400000);
+    } else if (d == 0 && ((V.word(g_accel.solid, x, y, z) >> BrickVolume::bit(x, y, z)) & 1ull)) {
       return true;
     }
     if (n >= rem) return false;  // the march runs out inside space known to be empty: a miss
@@ -316,7 +331,7 @@ RM_SD_INLINE JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float
 RM_DEV float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
   const float3 delta = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
   const float sm = fmaxf(fmaxf(fabsf(delta.x) * (float)o.rx, fabsf(delta.y) * (float)o.ry), fabsf(delta.z) * (float)o.rz);
-  invS = sm > 1e-12f ? __fdividef(1.0f, sm) : 1e12f;
+  invS = sm > 5e-4f ? __fdividef(1.0f, sm) : 2000.0f;  // capped: (d-1)*cell*invS <= 31*64*2000 < 2^22 in march_fast
   return delta;
 }
 
@@ -407,6 +422,18 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
       j.hit = false;
       j.closer = false;
       cut = false;
+      // A ray that is past the box (or never meets it) and does not descend only sees the ground
+      // from here on, farther away at every step: every remaining evaluation advances it by at
+      // least g (fp32 rounding is monotone), none can converge, so if the remaining evaluations
+      // must carry it beyond maxDist the trace ends as a miss ("lit" for a shadow ray) -- and of a
+      // miss its consumers read nothing but that fact (renderer.cl:252-255, 292-301, 389-392,
+      // 413-416: distance 1000, objectID -1). 1% covers the rounding of <= 2^16 additions.
+      if (r.distance > tout && rd.y >= 0.0f && g > o.eps && g < 1e5f && maxSteps < 65536 &&
+          (float)(maxSteps + 1) * g * 0.99f >= maxDist - r.distance) {
+        RM_STAT_EVENT(17);
+        r.distance = maxDist;
+        break;
+      }
     } else {
       int limit = o.maxVoxelIter;
       if (!kCount) {
@@ -502,23 +529,38 @@ RM_DEV float ambient_occlusion(Scene& s, const Vol& V, float3 pos, float3 n0) {
     d += o.aoStepDist;
     seed += 37u;
     const float3 n = unit3(table_xyz(s, seed) * 0.2f + n0);
-    float invS;
-    const int msteps = o.maxVoxelIter / 2;
-    const float3 delta = march_delta(o, n, msteps, invS);
-    // A probe changes ao only through max((d - h)*aoAmp/d, 0), which is 0 (factor exactly 1) for
-    // every h >= d when aoAmp >= 0: a voxel hit whose distance len - voxelSize is >= d, and the
-    // ground plane beyond d, are the same as no hit at all. Sample k of the march lies k world
-    // steps from the probe origin, so only the first (d + voxelSize)/step samples can matter;
-    // the production kernels march those (plus two for rounding), the counting kernels all of
-    // them like the reference (renderer.cl:342 marches maxVoxelIter/2 = 96 samples per probe).
-    int limit = msteps;
-    if (!kCount && o.aoAmp >= 0.0f && d > 0.0f) {
-      const float k = (d + o.voxelSize) * 1.01f / len3(delta * o.voxelBounds2);
-      if (k < (float)msteps) limit = f2i_sat(k) + 2 < msteps ? f2i_sat(k) + 2 : msteps;
+    const float3 q = n * d + pos;
+    float hdist;
+    // Probe origins that lie farther from the voxel box than d + voxelSize along some axis (ground
+    // far from the object): whatever the march might hit is at least that far away, i.e. beyond
+    // the distance d up to which a hit matters, and the call returns the ground pair or an
+    // equivalent one. 1e-3 dwarfs the fp32 error of the slab test at these magnitudes.
+    const float out = fmaxf(fmaxf(fmaxf(o.boundsMin.x - q.x, q.x - o.boundsMax.x), fmaxf(o.boundsMin.y - q.y, q.y - o.boundsMax.y)),
+                            fmaxf(o.boundsMin.z - q.z, q.z - o.boundsMax.z));
+    if (!kCount && o.aoAmp >= 0.0f && d > 0.0f && out > d + o.voxelSize + 1e-3f && out < 1e3f) {
+      RM_STAT_EVENT(18);
+      const float g = q.y + o.groundY;
+      hdist = g < 1e5f ? g : 1e5f;
+    } else {
+      float invS;
+      const int msteps = o.maxVoxelIter / 2;
+      const float3 delta = march_delta(o, n, msteps, invS);
+      // A probe changes ao only through max((d - h)*aoAmp/d, 0), which is 0 (factor exactly 1) for
+      // every h >= d when aoAmp >= 0: a voxel hit whose distance len - voxelSize is >= d, and the
+      // ground plane beyond d, are the same as no hit at all. Sample k of the march lies k world
+      // steps from the probe origin, so only the first (d + voxelSize)/step samples can matter;
+      // the production kernels march those (plus two for rounding), the counting kernels all of
+      // them like the reference (renderer.cl:342 marches maxVoxelIter/2 = 96 samples per probe).
+      int limit = msteps;
+      if (!kCount && o.aoAmp >= 0.0f && d > 0.0f) {
+        const float k = (d + o.voxelSize) * 1.01f / len3(delta * o.voxelBounds2);
+        if (k < (float)msteps) limit = f2i_sat(k) + 2 < msteps ? f2i_sat(k) + 2 : msteps;
+      }
+      RM_STAT_EVENT(11);
+      RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16 + 8 + i);
+      hdist = scene_distance<kCount>(s, V, q, n, delta, limit, invS, false).dist;
     }
-    RM_STAT_EVENT(11);
-    const JobResult h = scene_distance<kCount>(s, V, n * d + pos, n, delta, limit, invS, false);
-    ao *= 1.0f - cl_max((d - h.dist) * o.aoAmp / d, 0.0f);
+    ao *= 1.0f - cl_max((d - hdist) * o.aoAmp / d, 0.0f);
   }
   return ao;
 }
@@ -553,6 +595,7 @@ RM_OL_INLINE float3 object_lighting(Scene& s, const Vol& V, const PixelState& st
       const bool irrelevant = !kCount && kd == 0.0f && ks == 0.0f && zero.x == 0.0f && zero.y == 0.0f && zero.z == 0.0f;
       if (!irrelevant) {
         Isec sh;
+        RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16 + 1 + i);
         sphere_trace<kCount>(s, V, ipos + ldir * o.shadowBias, ldir, sh, lmax, o.shadowIter, false, false);
         const float sf = sh.distance < lmax ? 0.0f : 1.0f;
         if (sf > 0.0f) {
@@ -573,6 +616,7 @@ RM_DEV int mat_index(int id) { return id < 0 ? 0 : (id > 3 ? 3 : id); }
 template <bool kCount, class Vol>
 RM_DEV float3 bounce_color(Scene& s, const Vol& V, const PixelState& st, float3 ro, float3 rd, Isec& isec) {
   const RmOpts& o = g_opts;
+  RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16);
   sphere_trace<kCount>(s, V, ro, rd, isec, o.maxDist, o.maxIter, false, true);
   float3 col;
   if (isec.objectID < 0) {
@@ -589,6 +633,8 @@ template <bool kCount, class Vol>
 RM_DEV float3 scene_color(Scene& s, const Vol& V, const PixelState& st, float3 ro, float3 rd) {
   const RmOpts& o = g_opts;
   Isec isec;
+  RM_STAT_LEVEL(0);
+  RM_STAT_SITE(0);
   sphere_trace<kCount>(s, V, ro, rd, isec, o.maxDist, o.maxIter, true, true);
   float3 col;
   if (isec.distance >= o.maxDist) {
@@ -605,6 +651,7 @@ RM_DEV float3 scene_color(Scene& s, const Vol& V, const PixelState& st, float3 r
       for (int i = 0; i < o.reflectIter; ++i) {
         bd = reflect3(bd, ri.normal);
         const float3 bo = ri.pos + bd * 0.0075f;
+        RM_STAT_LEVEL(i + 1);
         reflectCol = reflectCol + bounce_color<kCount>(s, V, st, bo, bd, ri);
         if (ri.objectID < 0) break;
         if (o.mat[mat_index(ri.objectID)].r0 < 0.001f) break;
@@ -612,6 +659,7 @@ RM_DEV float3 scene_color(Scene& s, const Vol& V, const PixelState& st, float3 r
     } else {
       reflectCol = sky(o, reflect3(rd, n));
     }
+    RM_STAT_LEVEL(0);
     col = object_lighting<kCount>(s, V, st, rd, isec.pos, m, n, reflectCol);
   }
   return atmosphere(s, st, ro, rd, isec.distance, col);

@@ -56,6 +56,7 @@ struct RmAccel {
   int mx, my, mz;             // macro-cell grid extents = ceil(res / cell)
   int cell_shift;             // macro-cell edge = 1 << cell_shift voxels (>= 2)
   float cellf;                // (float)(1 << cell_shift)
+  float rxf, ryf, rzf;        // (float) of the grid extents: the march multiplies by them at every lookup
 };
 
 struct RmAccelStorage {  // owner of the device arrays behind an RmAccel view

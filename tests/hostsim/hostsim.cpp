@@ -18,13 +18,20 @@ struct SimStats {
   unsigned long long lookups, skips, skipped_samples, jumps, jump_samples, seq_adds, marches, traces, hist[16], events[32];
 };
 static thread_local SimStats t_stats;
-#define RM_STAT_LOOKUP() (t_stats.lookups++)
-#define RM_STAT_SKIP(n) (t_stats.skips++, t_stats.skipped_samples += (n), t_stats.hist[stat_bucket(n)]++)
+// per call site cost model of one pixel-sample (instruction estimates: cheap evaluation 15, full
+// distanceToScene call 150, march lookup 50, skipped sample 3)
+static thread_local float t_site_cost[64];
+static thread_local int t_site, t_level;
+#define RM_STAT_SITE(id) (t_site = (id) & 63)
+#define RM_STAT_LEVEL(l) (t_level = (l))
+#define RM_STAT_LEVEL_GET() t_level
+#define RM_STAT_LOOKUP() (t_stats.lookups++, t_site_cost[t_site] += 50.0f)
+#define RM_STAT_SKIP(n) (t_stats.skips++, t_stats.skipped_samples += (n), t_stats.hist[stat_bucket(n)]++, t_site_cost[t_site] += 3.0f * (n))
 #define RM_STAT_JUMP(n) (t_stats.jumps++, t_stats.jump_samples += (n))
 #define RM_STAT_SEQ(n) (t_stats.seq_adds += (n))
 #define RM_STAT_MARCH() (t_stats.marches++)
 #define RM_STAT_TRACE() (t_stats.traces++)
-#define RM_STAT_EVENT(id) (t_stats.events[(id)]++)
+#define RM_STAT_EVENT(id) (t_stats.events[(id)]++, t_site_cost[t_site] += ((id) == 0 ? 150.0f : ((id) == 12 ? 15.0f : 0.0f)))
 static inline int stat_bucket(int n) {
   int b = 0;
   while (n > 1 && b < 15) { n >>= 1; ++b; }
@@ -82,6 +89,7 @@ void build_accel(const uint8_t* vox, int rx, int ry, int rz, int iso, int cell_s
   a.cell_shift = cell_shift < 2 ? 2 : cell_shift;
   const int cell = 1 << a.cell_shift;
   a.cellf = (float)cell;
+  a.rxf = (float)rx; a.ryf = (float)ry; a.rzf = (float)rz;
   a.mx = (rx + cell - 1) >> a.cell_shift; a.my = (ry + cell - 1) >> a.cell_shift; a.mz = (rz + cell - 1) >> a.cell_shift;
   A.solid.assign((size_t)a.bx * a.by * a.bz, 0);
   A.occ.assign(A.solid.size(), 0);
@@ -131,6 +139,7 @@ void build_accel(const uint8_t* vox, int rx, int ry, int rz, int iso, int cell_s
   a.dist = A.dist.data();
 }
 
+float* g_cost_out = nullptr;  // optional: count x 64 floats, per-site cost of every rendered pixel-sample
 HostAccel g_host_accel;
 const uint8_t* g_accel_vox = nullptr;
 int g_accel_key[5] = {0, 0, 0, -1, -1};
@@ -168,6 +177,8 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
     for (int k = 0; k < count; ++k) {
       const int id = ids ? ids[k] : k;
       plain::Scene s(vox, reinterpret_cast<const float4*>(mc));
+      std::memset(t_site_cost, 0, sizeof t_site_cost);
+      t_site = 0; t_level = 0;
       float3 c;
       if (mode == 0) c = plain::render_pixel_sample<false>(s, plain::BrickVolume{}, id);
       else if (mode == 1) c = plain::render_pixel_sample<true>(s, plain::BrickVolume{}, id);
@@ -176,6 +187,7 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
       const float3 m = lerp3(make_float3(px[0], px[1], px[2]), c, o.frameBlend);  // mix(), renderer.cl:492
       px[0] = m.x; px[1] = m.y; px[2] = m.z; px[3] = 1.0f;
       cs += s.w.steps; ct += s.w.taps; co += s.w.outer;
+      if (g_cost_out) std::memcpy(g_cost_out + 64 * (size_t)k, t_site_cost, sizeof t_site_cost);
     }
 #pragma omp critical
     {
@@ -187,6 +199,7 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
   if (counters) { counters[0] += cs; counters[1] += ct; counters[2] += co; }
 }
 
+void sim_set_cost_buffer(float* p) { g_cost_out = p; }
 int sim_stats_words(void) { return (int)(sizeof(SimStats) / 8); }
 void sim_get_stats(unsigned long long* out, int reset) {
   std::memcpy(out, &g_total, sizeof g_total);

@@ -16,6 +16,11 @@ EXTRA_SCENES = {
     "blob_96": dict(vres=96, width=40, height=24, iters=2, mat="metal", volume="blob"),
     "empty_32": dict(vres=32, width=24, height=16, iters=1, mat="ao", volume="empty"),
     "full_32": dict(vres=32, width=24, height=16, iters=1, mat="metal", volume="full"),
+    # mid-size frames: every shortcut of the production routine fires thousands of times
+    "gyroid256_metal_240x136": dict(vres=256, width=240, height=136, iters=2, mat="metal"),
+    "gyroid256_ao_close": dict(vres=256, width=160, height=90, iters=2, mat="ao", theta=200.0, dist=1.2),
+    "blob192_ground_in_box": dict(vres=192, width=160, height=90, iters=2, mat="metal", volume="blob", groundY=0.5),
+    "stripes128_dof": dict(vres=128, width=160, height=90, iters=2, mat="orange-stripes", theta=30.0, dof=0.025),
 }
 
 

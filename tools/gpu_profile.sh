@@ -10,6 +10,7 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
 fi
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_c2.json 2> gpurun_out/${TAG}_bench_c2.err
 echo "bench rc=$?"; cut -c1-400 gpurun_out/${TAG}_bench_c2.json
+[ "${SKIP_NCU:-0}" = "1" ] && exit 0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e \
   > gpurun_out/${TAG}_launches_bench.log 2>&1
