@@ -27,7 +27,15 @@ RM_DEV float3 cross3(float3 a, float3 b) {
 }
 RM_DEV float len3(float3 a) { return sqrtf(dot3(a, a)); }
 // normalize(0) = 0 (pinned)
-RM_DEV float3 unit3(float3 a) {
+// Shared, NOT inlined (like light_pos and atmosphere in rm_scene_plain.cuh): three IEEE divisions
+// and a square root per call site add up; the render kernel's code (~60 KB) is larger than the
+// 32 KB L1.5 instruction cache, instruction-fetch stalls are its top stall reason, and every KB
+// taken out of it shows (B200, C2: unit3 41.0 -> 39.5, + atmosphere 39.1, + light_pos 38.4 ms).
+#define RM_SHARED_FN static __device__ __noinline__
+#ifndef RM_UNIT3_ATTR
+#define RM_UNIT3_ATTR RM_SHARED_FN
+#endif
+RM_UNIT3_ATTR float3 unit3(float3 a) {
   const float l = len3(a);
   return l == 0.0f ? a : a / l;
 }

@@ -328,7 +328,10 @@ RM_SD_INLINE JobResult scene_distance(Scene& s, const Vol& V, float3 rpos, float
 }
 
 // per-direction constants of the march: delta (renderer.cl:215) and 1 / (largest step in voxels)
-RM_DEV float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
+#ifndef RM_MDELTA_ATTR
+#define RM_MDELTA_ATTR RM_DEV  // (sharing this one too measured slower: 40.0 vs 39.1 ms)
+#endif
+RM_MDELTA_ATTR float3 march_delta(const RmOpts& o, float3 dir, int steps, float& invS) {
   const float3 delta = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
   const float sm = fmaxf(fmaxf(fabsf(delta.x) * (float)o.rx, fabsf(delta.y) * (float)o.ry), fabsf(delta.z) * (float)o.rz);
   invS = sm > 5e-4f ? __fdividef(1.0f, sm) : 2000.0f;  // capped: (d-1)*cell*invS <= 31*64*2000 < 2^22 in march_fast
@@ -478,7 +481,10 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
 RM_DEV float3 sky(const RmOpts& o, float3 d) { return lerp3(o.sky1, o.sky2, d.y * 0.5f + 0.5f); }  // :259-261
 
 // renderer.cl:263-269
-RM_DEV float3 light_pos(const Scene& s, const PixelState& st, int i) {
+#ifndef RM_LPOS_ATTR
+#define RM_LPOS_ATTR RM_SHARED_FN  // see unit3 in rm_math.cuh
+#endif
+RM_LPOS_ATTR float3 light_pos(const Scene& s, const PixelState& st, int i) {
   const uint32_t seed = f2u_wrap(st.px * 1957.0f + st.py * 2173.0f + s.time * 4763.742f);
   return table_xyz(s, seed) * g_opts.lightScatter + g_opts.lightPos[i];
 }
@@ -486,7 +492,10 @@ RM_DEV float3 light_pos(const Scene& s, const PixelState& st, int i) {
 RM_DEV float3 reflect3(float3 v, float3 n) { return v - n * (2.0f * dot3(v, n)); }  // :271-273
 
 // renderer.cl:275-290
-RM_DEV float3 atmosphere(const Scene& s, const PixelState& st, float3 ro, float3 rd, float distance, float3 col) {
+#ifndef RM_ATMO_ATTR
+#define RM_ATMO_ATTR RM_SHARED_FN  // two call sites (primary, bounce); see unit3 in rm_math.cuh
+#endif
+RM_ATMO_ATTR float3 atmosphere(const Scene& s, const PixelState& st, float3 ro, float3 rd, float distance, float3 col) {
   const RmOpts& o = g_opts;
   const float fa = 1.0f - expf(distance * distance * -o.fogPow);
   col = (sky(o, rd) - col) * fa + col;
