@@ -134,6 +134,12 @@ int rm_generate_gyroid_volume(rm_ctx* ctx, int rx, int ry, int rz);
 /* gen/generate-scatter-offsets (generators.clj:8-16) for java.util.Random seeds seed0 .. seed0+count-1
  * (the reference seeds from nanoTime) into the resident table slots 0 .. count-1. */
 int rm_generate_scatter_tables(rm_ctx* ctx, int64_t seed0, int count);
+/* meshvoxel/voxelize (ks < 0; meshvoxel.clj:60-69) and meshvoxel/voxelize-ks (ks >= 0; :45-58) on the
+ * device: `xyz` = n_points mesh vertices (3 floats each, e.g. from mio/read-stl :12-14) are mapped
+ * into a res^3 grid by mesh-scale (:16-23, fp64 like the JVM) and splatted with value 255 (single
+ * voxel, or a (2ks+1)^3 cube clamped to the grid). The result replaces the context's volume.
+ * NaN / infinite coordinates are rejected with RM_ERR_INVALID_ARG. */
+int rm_voxelize_points(rm_ctx* ctx, const float* xyz, int64_t n_points, int res, int ks);
 /* Parity hook: copy the resident volume (rx*ry*rz bytes) to the host. */
 int rm_read_volume(rm_ctx* ctx, uint8_t* voxels_out);
 

@@ -151,6 +151,17 @@ class CpuRenderer:
                             float(max_dist), int(max_steps), int(smooth), out)
         return out
 
+    def voxelize_points(self, vertices, res: int, ks: int = -1) -> np.ndarray:
+        """meshvoxel.clj voxelize (ks < 0) / voxelize-ks restated in oracle/meshvoxel_oracle.c (C restatement only)."""
+        fn = self.lib.orc_voxelize_points
+        fn.argtypes = [_f32p, C.c_longlong, C.c_int, C.c_int, _u8p]
+        fn.restype = C.c_int
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(res * res * res, dtype=np.uint8)
+        if fn(v.reshape(-1), v.shape[0], int(res), int(ks), out) != 0:
+            raise ValueError("NaN or infinite coordinate")
+        return out.reshape(res, res, res)
+
     def camera_ray(self, opts: bytes, mc: np.ndarray, pid: int) -> np.ndarray:
         out = np.zeros(8, dtype=np.float32)
         self._f("camera_ray")(opts, mc.reshape(-1), int(pid), out)

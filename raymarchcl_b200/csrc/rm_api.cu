@@ -488,6 +488,40 @@ int rm_generate_gyroid_volume(rm_ctx* c, int rx, int ry, int rz) {
   return RM_OK;
 }
 
+// meshvoxel/voxelize and voxelize-ks (meshvoxel.clj:45-69) on the device: the points (mesh vertices)
+// are scaled into the res^3 grid like mesh-scale (:16-23) and splatted with value 255.
+int rm_voxelize_points(rm_ctx* c, const float* xyz, int64_t n_points, int res, int ks) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!xyz || n_points <= 0 || n_points > (1ll << 40)) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: null points or bad count");
+  if (res <= 0 || res > 2048 || ks > 64) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: res must be 1..2048 and ks <= 64");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)res * res * res;
+  if (bytes > c->vox_capacity) {
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
+    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
+    c->vox_capacity = bytes;
+  }
+  float* d_xyz = nullptr;
+  int* d_bb = nullptr;
+  const size_t pbytes = (size_t)n_points * 3 * sizeof(float);
+  RM_CUDA(c, cudaMalloc(&d_xyz, pbytes));
+  cudaError_t e = cudaMalloc(&d_bb, 8 * sizeof(int));
+  int bad = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_xyz, xyz, pbytes, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = rm_launch_voxelize_points(d_xyz, (long long)n_points, res, ks, d_bb, c->d_vox, &bad, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_xyz);
+  cudaFree(d_bb);
+  if (e != cudaSuccess) return cuda_fail(c, e, "point voxeliser");
+  c->rx = c->ry = c->rz = res;
+  c->accel.valid = false;
+  if (bad) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: NaN or infinite coordinate");
+  c->stats.h2d_bytes += pbytes;
+  c->stats.kernel_launches += 2;
+  return RM_OK;
+}
+
 // Parity hook: read the resident volume back.
 int rm_read_volume(rm_ctx* c, uint8_t* voxels_out) {
   if (!c) return RM_ERR_INVALID_ARG;

@@ -6,6 +6,7 @@
 // fp64 (this library is compiled -fmad=false; fp64 sqrt and division are IEEE), and the tests
 // compare them with it byte for byte.
 #include "rm_kernels.h"
+#include <cstring>
 
 namespace {
 
@@ -88,6 +89,80 @@ k_scatter_tables(long long seed0, int tables, float4* __restrict__ out) {
       make_float4((float)(v[0] * m), (float)(v[1] * m), (float)(v[2] * m), (float)(v[3] * m));
 }
 
+
+// ---- mesh point-splat voxeliser (meshvoxel.clj:16-69) ----
+// floats as order-preserving ints, so that atomicMin / atomicMax give the bounding box
+__device__ __forceinline__ int f_ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+
+// bounding box of the points (gu/bounding-box, meshvoxel.clj:18); bb[0..2] = min, bb[3..5] = max
+// as ordered ints; bb[6] |= 1 when a coordinate is NaN or infinite
+__global__ void __launch_bounds__(256)
+k_points_bbox(const float* __restrict__ xyz, long long n, int* __restrict__ bb) {
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    for (int k = 0; k < 3; ++k) {
+      const float v = __ldg(xyz + 3 * i + k);
+      bad = bad || !(fabsf(v) <= 3.0e38f);
+      lo[k] = fminf(lo[k], v);
+      hi[k] = fmaxf(hi[k], v);
+    }
+  for (int k = 0; k < 3; ++k)
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_down_sync(0xffffffffu, lo[k], off));
+      hi[k] = fmaxf(hi[k], __shfl_down_sync(0xffffffffu, hi[k], off));
+    }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(bb + 6, 1);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 3; ++k) {
+      atomicMin(bb + k, f_ord(lo[k]));
+      atomicMax(bb + 3 + k, f_ord(hi[k]));
+    }
+}
+
+struct SplatParams {  // mesh-scale (meshvoxel.clj:16-23), evaluated once on the host in fp64
+  double p[3], off[3], s;
+  int res, ks;  // ks < 0: `voxelize` (one voxel, points outside the grid dropped); else `voxelize-ks`
+};
+
+// Clojure's (int x) on a double: truncation toward zero; NaN -> 0. (The JVM throws beyond the int
+// range; here such values saturate, which only ever happens for degenerate clouds.)
+__device__ __forceinline__ int clj_int(double v) {
+  if (!(v == v)) return 0;
+  if (v >= 2147483647.0) return 2147483647;
+  if (v <= -2147483648.0) return (-2147483647 - 1);
+  return (int)v;
+}
+
+// one thread per (point, z-slice of its splat): writes are idempotent (always 255), no atomics
+__global__ void __launch_bounds__(256)
+k_splat_points(const float* __restrict__ xyz, long long n, const __grid_constant__ SplatParams P, uint8_t* __restrict__ vox) {
+  const int slices = P.ks < 0 ? 1 : 2 * P.ks + 1;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= n * slices) return;
+  const long long i = t / slices;
+  const int dz = (int)(t - i * slices);
+  int c[3];
+  for (int k = 0; k < 3; ++k) {
+    const double v = (double)__ldg(xyz + 3 * i + k);
+    c[k] = clj_int(P.off[k] + (v - P.p[k]) * P.s);  // (g/+ off (g/* (g/- v p) s)), then (map int ..)
+  }
+  const int res = P.res;
+  const size_t rxy = (size_t)res * res;
+  if (P.ks < 0) {  // voxelize (meshvoxel.clj:60-69)
+    if (c[0] >= 0 && c[0] < res && c[1] >= 0 && c[1] < res && c[2] >= 0 && c[2] < res)
+      vox[(size_t)c[2] * rxy + (size_t)c[1] * res + c[0]] = 255;
+    return;
+  }
+  // voxelize-ks (meshvoxel.clj:45-58): ranges clamped to the grid
+  const long long z = (long long)c[2] - P.ks + dz;
+  if (z < 0 || z >= res) return;
+  const long long y0 = max((long long)c[1] - P.ks, 0ll), y1 = min((long long)c[1] + P.ks + 1, (long long)res);
+  const long long x0 = max((long long)c[0] - P.ks, 0ll), x1 = min((long long)c[0] + P.ks + 1, (long long)res);
+  for (long long y = y0; y < y1; ++y)
+    for (long long x = x0; x < x1; ++x) vox[(size_t)z * rxy + (size_t)y * res + (size_t)x] = 255;
+}
+
 }  // namespace
 
 cudaError_t rm_launch_gyroid(int rx, int ry, int rz, double* d_trig, uint8_t* d_vox, cudaStream_t stream) {
@@ -106,5 +181,38 @@ cudaError_t rm_launch_scatter_tables(long long seed0, int tables, float4* d_tabl
   if (tables <= 0) return cudaSuccess;
   const dim3 grid((RM_TABLE_MASK + 1 + 255) / 256, (unsigned)tables);
   k_scatter_tables<<<grid, 256, 0, stream>>>(seed0, tables, d_tables);
+  return cudaGetLastError();
+}
+
+static float ord_to_float(int i) { i ^= (i >> 31) & 0x7fffffff; float f; memcpy(&f, &i, 4); return f; }
+
+cudaError_t rm_launch_voxelize_points(const float* d_xyz, long long n, int res, int ks, int* d_bb, uint8_t* d_vox,
+                                      int* bad_input, cudaStream_t stream) {
+  *bad_input = 0;
+  cudaError_t e;
+  const int init[7] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0};
+  if ((e = cudaMemcpyAsync(d_bb, init, sizeof init, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(d_vox, 0, (size_t)res * res * res, stream)) != cudaSuccess) return e;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  k_points_bbox<<<blocks, 256, 0, stream>>>(d_xyz, n, d_bb);
+  int bb[7];
+  if ((e = cudaMemcpyAsync(bb, d_bb, sizeof bb, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+  if (bb[6]) { *bad_input = 1; return cudaSuccess; }
+  // mesh-scale (meshvoxel.clj:16-23) in fp64, in the reference's order of operations
+  SplatParams P;
+  double size[3], md = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    P.p[k] = (double)ord_to_float(bb[k]);
+    size[k] = (double)ord_to_float(bb[3 + k]) - P.p[k];
+  }
+  md = size[0] > size[1] ? size[0] : size[1];  // (max sx sy sz)
+  md = md > size[2] ? md : size[2];
+  for (int k = 0; k < 3; ++k) P.off[k] = (0.5 * (double)res) * (1.0 - size[k] / md);
+  P.s = (double)res / md;
+  P.res = res;
+  P.ks = ks;
+  const long long threads = n * (ks < 0 ? 1 : 2 * ks + 1);
+  k_splat_points<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_xyz, n, P, d_vox);
   return cudaGetLastError();
 }

@@ -76,3 +76,8 @@ cudaError_t rm_launch_render_warp(const RmOpts& opts, const RmShard& shard, cons
 cudaError_t rm_launch_gyroid(int rx, int ry, int rz, double* d_trig, uint8_t* d_vox, cudaStream_t stream);
 // generate-scatter-offsets (generators.clj:8-16) for java.util.Random seeds seed0 .. seed0+tables-1.
 cudaError_t rm_launch_scatter_tables(long long seed0, int tables, float4* d_tables, cudaStream_t stream);
+// mesh-scale + voxelize / voxelize-ks (meshvoxel.clj:16-69) of n points (d_xyz: 3n floats) into d_vox (res^3 bytes,
+// zero-filled first). ks < 0 = `voxelize`, else `voxelize-ks`. d_bb: 7 ints of scratch. Synchronises the stream.
+// *bad_input is set when a coordinate is NaN / infinite (nothing is splatted then).
+cudaError_t rm_launch_voxelize_points(const float* d_xyz, long long n, int res, int ks, int* d_bb, uint8_t* d_vox,
+                                      int* bad_input, cudaStream_t stream);

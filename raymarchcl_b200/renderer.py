@@ -93,6 +93,13 @@ class Renderer:
         self._check(self._lib.rm_generate_gyroid_volume(self._h, rx, ry, rz))
         self.vres = (rx, ry, rz)
 
+    def voxelize_points(self, vertices, res: int, ks: int = -1) -> None:
+        """``meshvoxel/voxelize`` (``ks < 0``, meshvoxel.clj:60-69) or ``meshvoxel/voxelize-ks``
+        (meshvoxel.clj:45-58) of mesh vertices on the device; the result becomes the volume."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        self._check(self._lib.rm_voxelize_points(self._h, v.ctypes.data, v.shape[0], int(res), int(ks)))
+        self.vres = (int(res),) * 3
+
     def generate_scatter_tables(self, seed0: int, count: int) -> None:
         """``generate-scatter-offsets`` for seeds seed0..seed0+count-1 into the resident table slots."""
         self._check(self._lib.rm_generate_scatter_tables(self._h, int(seed0), int(count)))
