@@ -61,7 +61,7 @@ L2_FLUSH_BYTES = 512 << 20  # > 126 MB L2
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -104,7 +104,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -122,9 +122,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.1:
-                continue
+        inside = [(ts, line) for ts, line in self.rows if t0 <= ts <= t1 + 0.02]
+        if not inside and self.rows:  # a timed region shorter than the polling period: take the nearest sample
+            inside = [min(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+        for ts, line in inside:
             f = [x.strip() for x in line.split(",")]
             try:
                 sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
@@ -285,12 +286,12 @@ def run_b200(args):
         steps_frame, taps_frame, outer_frame = [int(x) for x in work.tolist()]
 
         # ---- device-resident timed loop ----
+        sampler = ClockSampler(local) if rank == 0 else None  # polling starts during the warm-up
         for _ in range(args.warmup):
             resident_frame()
             flush.zero_()
         barrier()
         r.reset_stats()
-        sampler = ClockSampler(local) if rank == 0 else None
         t_wall0 = time.perf_counter()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for a, b in ev:

@@ -19,3 +19,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_re
   -o gpurun_out/${TAG}_bricks_c2s python bench.py --workload c2s --steps 1 --warmup 1 --no-cpu-baseline --no-e2e \
   > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"; ls -la gpurun_out
+if [ "${FULL_C2:-0}" = "1" ]; then
+  # full-size capture of one render launch (all 16 passes of the 1080p frame): dram__bytes for roofline.traffic
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_bricks -s 1 -c 1 -f \
+    -o gpurun_out/${TAG}_bricks_c2 python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e \
+    > gpurun_out/${TAG}_ncu_full_c2.log 2>&1
+  echo "ncu full c2 rc=$?"
+fi
