@@ -395,8 +395,9 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
   const float3 delta = march_delta(o, rd, o.maxVoxelIter, invS);
   JobResult j;
   j.g = 0.0f; j.dist = 0.0f; j.hit = false; j.closer = false; j.p = f3s(0.0f);
-  r.distance = o.startDist;
-  r.pos = ro;
+  // the trace state lives in registers; `r` (the caller's memory) is written once at the end
+  float dist = o.startDist;
+  float3 pos = ro;
   // distanceToScene returns min(voxel distance, ground distance g): a voxel hit whose distance
   // len - voxelSize is >= g returns the same pair as no hit, so only the samples within
   // g + voxelSize of the ray position can change the returned distance; for a shadow ray
@@ -416,9 +417,9 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
   while (--maxSteps >= 0) {
     if (kCount) s.w.outer++;
     RM_STAT_EVENT(wantSurface ? 8 : 9);
-    r.pos = ro + rd * r.distance;
-    const float g = r.pos.y + o.groundY;
-    if (!kCount && (r.distance > tout || tin - r.distance > g * 1.0001f + 1e-3f || g <= 0.0f)) {
+    pos = ro + rd * dist;
+    const float g = pos.y + o.groundY;
+    if (!kCount && (dist > tout || tin - dist > g * 1.0001f + 1e-3f || g <= 0.0f)) {
       RM_STAT_EVENT(12);
       j.g = g;
       j.dist = g < 1e5f ? g : 1e5f;
@@ -431,10 +432,10 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
       // must carry it beyond maxDist the trace ends as a miss ("lit" for a shadow ray) -- and of a
       // miss its consumers read nothing but that fact (renderer.cl:252-255, 292-301, 389-392,
       // 413-416: distance 1000, objectID -1). 1% covers the rounding of <= 2^16 additions.
-      if (r.distance > tout && rd.y >= 0.0f && g > o.eps && g < 1e5f && maxSteps < 65536 &&
-          (float)(maxSteps + 1) * g * 0.99f >= maxDist - r.distance) {
+      if (dist > tout && rd.y >= 0.0f && g > o.eps && g < 1e5f && maxSteps < 65536 &&
+          (float)(maxSteps + 1) * g * 0.99f >= maxDist - dist) {
         RM_STAT_EVENT(17);
-        r.distance = maxDist;
+        dist = maxDist;
         break;
       }
     } else {
@@ -443,24 +444,26 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
         float reach = g;
         // (a hit just beyond the light must also be farther than eps, or it could end the trace as
         // "converged", i.e. shadowed, before the light is reached)
-        if (!wantSurface) reach = fminf(reach, fmaxf(maxDist - r.distance, o.eps));
+        if (!wantSurface) reach = fminf(reach, fmaxf(maxDist - dist, o.eps));
         const float k = (reach + o.voxelSize) * inv_step;
         cut = k < (float)(limit - 2);
         if (cut) limit = f2i_sat(k) + 2;
       }
-      j = scene_distance<kCount>(s, V, r.pos, rd, delta, limit, invS, smooth);
+      j = scene_distance<kCount>(s, V, pos, rd, delta, limit, invS, smooth);
     }
-    if (fabsf(j.dist) <= o.eps || r.distance >= maxDist) break;
-    r.distance += j.dist;
+    if (fabsf(j.dist) <= o.eps || dist >= maxDist) break;
+    dist += j.dist;
   }
   if (!kCount && wantSurface && cut && !j.hit) RM_STAT_EVENT(10);
   if (!kCount && wantSurface && cut && !j.hit)
-    j = scene_distance<kCount>(s, V, r.pos, rd, delta, o.maxVoxelIter, invS, smooth);
-  const bool miss = r.distance >= maxDist;
+    j = scene_distance<kCount>(s, V, pos, rd, delta, o.maxVoxelIter, invS, smooth);
+  const bool miss = dist >= maxDist;
   if (miss) {
-    r.pos = ro + rd * r.distance;
-    r.distance = 1000.0f;
+    pos = ro + rd * dist;
+    dist = 1000.0f;
   }
+  r.distance = dist;
+  r.pos = pos;
   r.objectID = -1;
   r.normal = f3s(0.0f);
   if (!wantSurface) return;  // shadow rays use the distance only
