@@ -131,6 +131,9 @@ int rm_set_stream(rm_ctx* ctx, void* cuda_stream);
 /* gen/make-gyroid-volume (generators.clj:27-42) straight into the context's volume; byte-identical
  * to the host generator raymarchcl_b200/generators.py:make_gyroid_volume. Replaces rm_set_volume. */
 int rm_generate_gyroid_volume(rm_ctx* ctx, int rx, int ry, int rz);
+/* gen/make-terrain (generators.clj:44-60) likewise; byte-identical to generators.py:make_terrain.
+ * Needs rz >= rx (the reference indexes its second wall with x as the slice). */
+int rm_generate_terrain_volume(rm_ctx* ctx, int rx, int ry, int rz);
 /* gen/generate-scatter-offsets (generators.clj:8-16) for java.util.Random seeds seed0 .. seed0+count-1
  * (the reference seeds from nanoTime) into the resident table slots 0 .. count-1. */
 int rm_generate_scatter_tables(rm_ctx* ctx, int64_t seed0, int count);

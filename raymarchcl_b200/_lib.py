@@ -25,7 +25,7 @@ RM_OPT_TRIP_LIMIT = 7
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_set_volume", "rm_load_volume_file", "rm_generate_gyroid_volume", "rm_voxelize_points", "rm_generate_scatter_tables", "rm_read_volume",
+    "rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_set_volume", "rm_load_volume_file", "rm_generate_gyroid_volume", "rm_generate_terrain_volume", "rm_voxelize_points", "rm_generate_scatter_tables", "rm_read_volume",
     "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
     "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
     "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_shard_slots", "rm_unpack_shards", "rm_set_option", "rm_get_stats",
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     lib.rm_set_volume.argtypes = [vp, vp, ip, ip, ip]
     lib.rm_load_volume_file.argtypes = [vp, C.c_char_p, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     lib.rm_generate_gyroid_volume.argtypes = [vp, ip, ip, ip]
+    lib.rm_generate_terrain_volume.argtypes = [vp, ip, ip, ip]
     lib.rm_voxelize_points.argtypes = [vp, vp, C.c_int64, ip, ip]
     lib.rm_generate_scatter_tables.argtypes = [vp, C.c_int64, ip]
     lib.rm_read_volume.argtypes = [vp, vp]

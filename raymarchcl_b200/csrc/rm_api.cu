@@ -488,6 +488,33 @@ int rm_generate_gyroid_volume(rm_ctx* c, int rx, int ry, int rz) {
   return RM_OK;
 }
 
+// gen/make-terrain (generators.clj:44-60) on the device.
+int rm_generate_terrain_volume(rm_ctx* c, int rx, int ry, int rz) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (rx <= 0 || ry <= 0 || rz < rx || (long long)rx * ry > 0x7fffffffLL)  // the reference's second wall needs rz >= rx
+    return fail(c, RM_ERR_INVALID_ARG, "rm_generate_terrain_volume: bad extents");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)rx * ry * rz;
+  if (bytes / 64 > 0x7fffffffULL) return fail(c, RM_ERR_INVALID_ARG, "rm_generate_terrain_volume: more than 2^37 voxels");
+  if (bytes > c->vox_capacity) {
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
+    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
+    c->vox_capacity = bytes;
+  }
+  double* d_trig = nullptr;
+  RM_CUDA(c, cudaMalloc(&d_trig, sizeof(double) * 2 * ((size_t)rx + ry + rz)));
+  cudaError_t e = rm_launch_terrain(rx, ry, rz, d_trig, c->d_vox, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_trig);
+  if (e != cudaSuccess) return cuda_fail(c, e, "terrain generator");
+  c->stats.kernel_launches += 3;
+  c->rx = rx; c->ry = ry; c->rz = rz;
+  c->accel.valid = false;
+  return RM_OK;
+}
+
+
 // meshvoxel/voxelize and voxelize-ks (meshvoxel.clj:45-69) on the device: the points (mesh vertices)
 // are scaled into the res^3 grid like mesh-scale (:16-23) and splatted with value 255.
 int rm_voxelize_points(rm_ctx* c, const float* xyz, int64_t n_points, int res, int ks) {

@@ -90,6 +90,35 @@ k_scatter_tables(long long seed0, int tables, float4* __restrict__ out) {
 }
 
 
+// make-terrain (generators.clj:44-60): two 4-voxel walls of value 64 up to y < int(ry*0.666), then
+// bumpy pillars of value 255 (they overwrite the walls): column (x, z) with dx = 16 - x%32,
+// dz = 16 - z%32, dx^2 + dz^2 <= 121 is filled for y <= int(ry*(0.25 + 0.125*sin(0.02 z)*cos(0.03 x))).
+// One thread per 4 voxels of a row.
+__global__ void __launch_bounds__(256)
+k_terrain(int rx, int ry, int rz, int ymax, const double* __restrict__ cosx, const double* __restrict__ sinz,
+          uint8_t* __restrict__ vox) {
+  const int qx = (rx + 3) >> 2;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)qx * ry * rz) return;
+  const int x0 = (int)(t % qx) * 4;
+  const int y = (int)((t / qx) % ry);
+  const int z = (int)(t / ((long long)qx * ry));
+  const int dz = 16 - (z % 32);
+  const double sz = sinz[z];
+  for (int k = 0; k < 4; ++k) {
+    const int x = x0 + k;
+    if (x >= rx) break;
+    int v = 0;
+    if (y < ymax && (z < 4 || (x >= rx - 4 && z < rx))) v = 64;  // second wall: index x'*rxy + y*rx + (rx-1-z'), x' < rx, z' < 4
+    const int dx = 16 - (x % 32);
+    if (dx * dx + dz * dz <= 121) {
+      const int h = (int)((double)ry * (0.25 + 0.125 * (sz * cosx[x])));
+      if (y <= h) v = 255;
+    }
+    vox[((size_t)z * ry + y) * rx + x] = (uint8_t)v;
+  }
+}
+
 // ---- mesh point-splat voxeliser (meshvoxel.clj:16-69) ----
 // floats as order-preserving ints, so that atomicMin / atomicMax give the bounding box
 __device__ __forceinline__ int f_ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
@@ -174,6 +203,16 @@ cudaError_t rm_launch_gyroid(int rx, int ry, int rz, double* d_trig, uint8_t* d_
   k_axis_trig<<<(rz + 127) / 128, 128, 0, stream>>>(rz, scl, 0.0, cz, sz);
   const long long n = (long long)((rx + 3) >> 2) * ry * rz;
   k_gyroid<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rx, ry, rz, cx, sx, cy, sy, cz, sz, d_vox);
+  return cudaGetLastError();
+}
+
+cudaError_t rm_launch_terrain(int rx, int ry, int rz, double* d_trig, uint8_t* d_vox, cudaStream_t stream) {
+  // d_trig: 2 * (rx + rz) doubles of scratch
+  double *cx = d_trig, *sx = cx + rx, *cz = sx + rx, *sz = cz + rz;
+  k_axis_trig<<<(rx + 127) / 128, 128, 0, stream>>>(rx, 0.03, 0.0, cx, sx);
+  k_axis_trig<<<(rz + 127) / 128, 128, 0, stream>>>(rz, 0.02, 0.0, cz, sz);
+  const long long n = (long long)((rx + 3) >> 2) * ry * rz;
+  k_terrain<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rx, ry, rz, (int)((double)ry * 0.666), cx, sz, d_vox);
   return cudaGetLastError();
 }
 

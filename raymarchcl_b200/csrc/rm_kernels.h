@@ -74,6 +74,9 @@ cudaError_t rm_launch_render_warp(const RmOpts& opts, const RmShard& shard, cons
 // ---- device-side input generators (rm_generate.cu) ----
 // make-gyroid-volume (generators.clj:27-42) into d_vox (rx*ry*rz bytes); d_trig = 2*(rx+ry+rz) doubles of scratch.
 cudaError_t rm_launch_gyroid(int rx, int ry, int rz, double* d_trig, uint8_t* d_vox, cudaStream_t stream);
+// make-terrain (generators.clj:44-60) into d_vox; d_trig = 2*(rx+rz) doubles of scratch. The reference indexes its
+// second wall as x*rx*ry + ..., x < rx: the caller must make sure rz >= rx (as the reference implicitly requires).
+cudaError_t rm_launch_terrain(int rx, int ry, int rz, double* d_trig, uint8_t* d_vox, cudaStream_t stream);
 // generate-scatter-offsets (generators.clj:8-16) for java.util.Random seeds seed0 .. seed0+tables-1.
 cudaError_t rm_launch_scatter_tables(long long seed0, int tables, float4* d_tables, cudaStream_t stream);
 // mesh-scale + voxelize / voxelize-ks (meshvoxel.clj:16-69) of n points (d_xyz: 3n floats) into d_vox (res^3 bytes,

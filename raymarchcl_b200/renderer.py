@@ -93,6 +93,12 @@ class Renderer:
         self._check(self._lib.rm_generate_gyroid_volume(self._h, rx, ry, rz))
         self.vres = (rx, ry, rz)
 
+    def generate_terrain_volume(self, vres) -> None:
+        """``make-terrain`` (generators.clj:44-60) on the device instead of host + upload."""
+        rx, ry, rz = [int(vres)] * 3 if isinstance(vres, (int, np.integer)) else [int(v) for v in vres]
+        self._check(self._lib.rm_generate_terrain_volume(self._h, rx, ry, rz))
+        self.vres = (rx, ry, rz)
+
     def voxelize_points(self, vertices, res: int, ks: int = -1) -> None:
         """``meshvoxel/voxelize`` (``ks < 0``, meshvoxel.clj:60-69) or ``meshvoxel/voxelize-ks``
         (meshvoxel.clj:45-58) of mesh vertices on the device; the result becomes the volume."""

@@ -389,6 +389,18 @@ def test_device_gyroid_generator_is_byte_identical_to_host_generator(gpu_rendere
     assert np.array_equal(got, want), f"{(got != want).sum()} voxels differ"
 
 
+@pytest.mark.parametrize("vres", [64, 256, (96, 40, 130)], ids=str)
+def test_device_terrain_generator_is_byte_identical_to_host_generator(gpu_renderer, vres):
+    from raymarchcl_b200 import make_terrain
+    gpu_renderer.generate_terrain_volume(vres)
+    got = gpu_renderer.read_volume()
+    want = make_terrain(vres)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), f"{(got != want).sum()} voxels differ"
+    with pytest.raises(Exception):
+        gpu_renderer.generate_terrain_volume((64, 64, 32))  # the reference's second wall needs rz >= rx
+
+
 def test_device_scatter_tables_reproduce_java_random(gpu_renderer):
     """Tables generated on the device (java.util.Random LCG, seeds 1000+i) drive a render that is
     bit-identical to the render from the host-generated tables."""
