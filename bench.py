@@ -58,6 +58,10 @@ TILE = (32, 32)
 L2_FLUSH_BYTES = 512 << 20  # > 126 MB L2
 
 
+def _emit(line: dict) -> None:  # replaced in main() by a writer to the real stdout
+    print(json.dumps(line), flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,7 +214,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_b200(args):
@@ -402,13 +406,21 @@ def run_b200(args):
                 "sample": f"every {stride}th pixel id of all {iters} passes ({len(ids)} pixels, {s_steps} inner steps)"}
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"error": str(e)}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there while we run
+    # (NCCL's version banner under NCCL_DEBUG=VERSION, for one) is sent to stderr instead.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line: dict) -> None:
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
