@@ -376,7 +376,9 @@ RM_DEV void march_window(const RmOpts& o, float3 ro, float3 rd, float maxDist, f
       b = fminf(b, fmaxf(t0, t1));
     }
   }
-  if (miss || b < a || b < 0.0f) { tin = kInf; tout = -kInf; return; }
+  // (a box wholly behind the origin, b < 0, needs no special case: every d > tout is "beyond" -- and a
+  // trace with a negative startDist may well begin inside it)
+  if (miss || b < a) { tin = kInf; tout = -kInf; return; }
   tin = a;
   tout = b;
 }
