@@ -122,11 +122,14 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
 #ifndef RM_NO_CARVEOUT
   // no shared memory is used: give the whole 256 KB of the SM's unified cache to L1 (the distance
   // map, the bit-bricks and the spill slots all live there)
-  static bool carveout_set = false;
-  if (!carveout_set) {
+  // (function attributes are per device: one flag per device, set on the first launch there)
+  static bool carveout_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !carveout_set[dev]) {
     cudaFuncSetAttribute(k_render_bricks<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_render_bricks<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    carveout_set = true;
+    carveout_set[dev] = true;
   }
 #endif
   cudaError_t e = cudaMemcpyToSymbolAsync(plain::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream);
