@@ -39,6 +39,7 @@ static inline int stat_bucket(int n) {
 }
 
 #include "rm_scene_plain.cuh"
+#include "rm_wave.cuh"
 
 namespace {
 
@@ -200,6 +201,70 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
 }
 
 void sim_set_cost_buffer(float* p) { g_cost_out = p; }
+// The wavefront stages of rm_wave.cuh run on the host in the launcher's order (rm_render_wave.cu):
+// primary; per level L: [finish(L-1)], prepare(L), all queued traces; finish(last); final.
+// mode: 0 = production routine, 1 = counting routine.
+void sim_render_pixels_wave(const uint8_t* vox, const float* mc, const void* opts544, float* pixels, int n,
+                            const int* ids, int nids, unsigned long long* counters, int mode, int cell_shift) {
+  RmOpts o;
+  std::memset(&o, 0, sizeof o);
+  decode_opts(opts544, &o);
+  const int key[5] = {o.rx, o.ry, o.rz, o.isoVal, cell_shift};
+  if (g_accel_vox != vox || std::memcmp(key, g_accel_key, sizeof key) != 0) {
+    build_accel(vox, o.rx, o.ry, o.rz, o.isoVal, cell_shift, g_host_accel);
+    g_accel_vox = vox;
+    std::memcpy(g_accel_key, key, sizeof key);
+  }
+  plain::g_accel = g_host_accel.view;
+  plain::g_opts = o;
+  const int count = ids ? nids : n;
+  const int lmax = std::min(o.reflectIter < 0 ? 0 : o.reflectIter, wave::kMaxLevels - 1);
+  std::vector<wave::WaveRec> rec((size_t)wave::kMaxLevels * count);
+  std::vector<float4> refl(count);
+  std::vector<float2> pxy(count);
+  std::vector<wave::WaveJob> jobs((size_t)(o.numLights + 1) * count + 1);
+  unsigned njobs = 0;
+  wave::WaveBuf B{rec.data(), refl.data(), pxy.data(), jobs.data(), &njobs, (unsigned)count, (unsigned)jobs.size()};
+  const float4* table = reinterpret_cast<const float4*>(mc);
+  unsigned long long cs = 0, ct = 0, co = 0;
+  const plain::BrickVolume V{};
+#define SIM_STAGE(BODY)                                                        \
+  _Pragma("omp parallel for schedule(dynamic, 64) reduction(+ : cs, ct, co)") \
+  for (int it = 0; it < count; ++it) {                                         \
+    plain::Scene s(vox, table);                                                \
+    BODY;                                                                      \
+    cs += s.w.steps; ct += s.w.taps; co += s.w.outer;                          \
+  }
+  if (mode == 0) { SIM_STAGE(wave::wave_primary<false>(B, (unsigned)it, s, V, ids ? ids[it] : it)) }
+  else { SIM_STAGE(wave::wave_primary<true>(B, (unsigned)it, s, V, ids ? ids[it] : it)) }
+  for (int L = 0; L <= lmax; ++L) {
+    njobs = 0;
+    if (mode == 0) { SIM_STAGE(if (L >= 2) wave::wave_finish<false>(B, (unsigned)it, s, L - 1); wave::wave_prepare<false>(B, (unsigned)it, s, V, L)) }
+    else { SIM_STAGE(if (L >= 2) wave::wave_finish<true>(B, (unsigned)it, s, L - 1); wave::wave_prepare<true>(B, (unsigned)it, s, V, L)) }
+    const int nj = (int)std::min<size_t>(njobs, jobs.size());
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : cs, ct, co)
+    for (int k = 0; k < nj; ++k) {
+      plain::Scene s(vox, table);
+      if (mode == 0) wave::wave_trace<false>(B, jobs[k], s, V);
+      else wave::wave_trace<true>(B, jobs[k], s, V);
+      cs += s.w.steps; ct += s.w.taps; co += s.w.outer;
+    }
+  }
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int it = 0; it < count; ++it) {
+    plain::Scene s(vox, table);
+    const int id = ids ? ids[it] : it;
+    float3 c;
+    if (mode == 0) { if (lmax >= 1) wave::wave_finish<false>(B, (unsigned)it, s, lmax); c = wave::wave_final<false>(B, (unsigned)it, s); }
+    else { if (lmax >= 1) wave::wave_finish<true>(B, (unsigned)it, s, lmax); c = wave::wave_final<true>(B, (unsigned)it, s); }
+    float* px = pixels + 4 * (size_t)id;
+    const float3 m = lerp3(make_float3(px[0], px[1], px[2]), c, o.frameBlend);
+    px[0] = m.x; px[1] = m.y; px[2] = m.z; px[3] = 1.0f;
+  }
+#undef SIM_STAGE
+  if (counters) { counters[0] += cs; counters[1] += ct; counters[2] += co; }
+}
+
 int sim_stats_words(void) { return (int)(sizeof(SimStats) / 8); }
 void sim_get_stats(unsigned long long* out, int reset) {
   std::memcpy(out, &g_total, sizeof g_total);

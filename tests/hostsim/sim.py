@@ -13,7 +13,7 @@ _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 
 STAT_NAMES = ["lookups", "skips", "skipped_samples", "jumps", "jump_samples", "seq_adds", "marches", "traces"]
-MODES = {"production": 0, "counting": 1, "bytes": 2}
+MODES = {"production": 0, "counting": 1, "bytes": 2, "wave": 0, "wave_counting": 1}
 
 
 class HostSim:
@@ -22,6 +22,8 @@ class HostSim:
         lib.sim_render_pixels.argtypes = [_u8p, _f32p, C.c_char_p, _f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                           C.c_int, C.c_int]
         lib.sim_render_pixels.restype = None
+        lib.sim_render_pixels_wave.argtypes = lib.sim_render_pixels.argtypes
+        lib.sim_render_pixels_wave.restype = None
         lib.sim_stats_words.restype = C.c_int
         lib.sim_get_stats.argtypes = [_u64p, C.c_int]
 
@@ -36,8 +38,9 @@ class HostSim:
         if ids is not None:
             ids = np.ascontiguousarray(ids, dtype=np.int32)
             idp, nid = ids.ctypes.data_as(C.c_void_p), int(ids.size)
+        fn = self.lib.sim_render_pixels_wave if mode.startswith("wave") else self.lib.sim_render_pixels
         for o, mc in zip(opts, mcs):
-            self.lib.sim_render_pixels(vox, np.ascontiguousarray(mc, dtype=np.float32).reshape(-1), o,
+            fn(vox, np.ascontiguousarray(mc, dtype=np.float32).reshape(-1), o,
                                        pixels.reshape(-1), width * height, idp, nid,
                                        counters.ctypes.data_as(C.c_void_p), MODES[mode], cell_shift)
         return pixels, counters
