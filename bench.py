@@ -69,7 +69,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="fast", choices=["fast", "plain", "warp"])
+    ap.add_argument("--kernel", default="fast", choices=["fast", "plain", "warp", "wave"])
     ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE",
                     help="rm_set_option tuning knob of the fast kernel (results do not depend on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -247,7 +247,7 @@ def run_b200(args):
 
     layout = ShardLayout(w, h, world, *TILE)
     r = Renderer(local)
-    r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2}[args.kernel])
+    r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2, "wave": 3}[args.kernel])
     for kv in args.opt:
         k, v = kv.split("=")
         r.set_option(int(k), int(v))
@@ -366,6 +366,7 @@ def run_b200(args):
             "peak_source": peak_src,
             "kernel": {"fast": "k_render_bricks (all passes of a frame in one launch)",
                        "warp": "k_render_warp (persistent, all passes of a frame in one launch)",
+                       "wave": "k_wave_* pipeline (primary, prepare / persistent trace per level, final)",
                        "plain": "k_render_plain (one launch per pass)"}[args.kernel],
             "algorithmic_bytes_per_frame": steps_frame + taps_frame,
             "kernel_ms_per_frame": kernel_s_per_frame * 1e3,

@@ -72,13 +72,15 @@ typedef enum rm_option {
   RM_OPT_COUNT_WORK = 1,   /* 0 (default) | 1: gather reference-equivalent work counters */
   RM_OPT_KERNEL = 2,       /* which RenderImage kernel: 0 = one thread per (pixel, pass) over the bit-brick
                               volume; 1 = plain, over the raw byte volume (comparison kernel);
-                              2 = warp-scheduled persistent state machine over the bit-brick volume.
-                              All three produce identical results. */
+                              2 = warp-scheduled persistent state machine over the bit-brick volume;
+                              3 = wavefront pipeline (stages + a persistent, refilling trace kernel).
+                              All four produce identical results. */
   /* tuning knobs of the fast kernel; none of them changes results */
   RM_OPT_CELL_SHIFT = 3,   /* macro-cell edge of the distance map = 1<<value voxels; 0 = auto (~res/64) */
   RM_OPT_FUSE_LIMIT = 6,   /* max passes rendered by one launch (1..32) */
-  RM_OPT_TRIP_LIMIT = 7    /* watchdog of kernel 2: scheduling trips a warp may take per launch before
+  RM_OPT_TRIP_LIMIT = 7,   /* watchdog of kernel 2: scheduling trips a warp may take per launch before
                               the launch is abandoned with RM_ERR_CUDA (default 2^28) */
+  RM_OPT_WAVE_CHUNK = 8    /* kernel 3: (pixel, pass) items per chunk of the pipeline (1024..2^24, default 2^21) */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */

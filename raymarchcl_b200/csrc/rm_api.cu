@@ -64,6 +64,8 @@ struct rm_ctx {
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
   int warp_blocks[2] = {0, 0};            // resident blocks per SM of the warp kernel [plain, counting]
+  RmWaveScratch wave;                     // scratch of the wavefront path (kernel 3)
+  unsigned wave_chunk = 1u << 21;         // items per chunk of the wavefront path
   int cell_shift_opt = 0;           // 0 = auto
   int fuse_limit = RM_MAX_FUSED_PASSES;
 
@@ -292,6 +294,11 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
                                   c->warp_blocks[variant] * c->num_sms, c->stream);
         if (e == cudaSuccess && m > 1)
           e = rm_launch_blend_passes(c->d_colour, blend, m, c->shard, c->W, c->H, c->d_accum, c->stream);
+      } else if (c->kernel_kind == 3 && rm_wave_supports(passes[i])) {
+        int launched = 0;
+        e = rm_launch_render_wave(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
+                                  c->d_colour, c->d_accum, cnt, &c->wave, c->num_sms, c->wave_chunk, &launched, c->stream);
+        c->stats.kernel_launches += launched - (m > 1 ? 2 : 1);  // (the common bookkeeping below adds that much)
       } else {
         e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
                                   c->d_colour, c->d_accum, cnt, c->stream);
@@ -394,6 +401,7 @@ void rm_destroy(rm_ctx* c) {
   for (EventPair& p : c->free_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_tables); cudaFree(c->d_counters);
   cudaFree(c->d_colour); cudaFree(c->d_queue); cudaFree(c->d_watchdog);
+  rm_wave_free(&c->wave);
   rm_accel_free(&c->accel);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -813,13 +821,17 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
   switch (option) {
     case RM_OPT_COUNT_WORK: c->count_work = value != 0; return RM_OK;
     case RM_OPT_KERNEL:
-      if (value < 0 || value > 2) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_KERNEL: 0 (bricks), 1 (plain) or 2 (warp)");
+      if (value < 0 || value > 3) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_KERNEL: 0 (bricks), 1 (plain), 2 (warp) or 3 (wavefront)");
       c->kernel_kind = (int)value;
       return RM_OK;
     case RM_OPT_CELL_SHIFT:
       if (value < 0 || value > 6 || value == 1) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_CELL_SHIFT: 0 (auto) or 2..6");
       c->cell_shift_opt = (int)value;
       c->accel.valid = false;
+      return RM_OK;
+    case RM_OPT_WAVE_CHUNK:
+      if (value < 1024 || value > (1ll << 24)) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_WAVE_CHUNK: 1024..2^24 items");
+      c->wave_chunk = (unsigned)value;
       return RM_OK;
     case RM_OPT_TRIP_LIMIT:
       if (value < 1 || value > 0xffffffffLL) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_TRIP_LIMIT: 1..2^32-1");

@@ -84,3 +84,23 @@ cudaError_t rm_launch_scatter_tables(long long seed0, int tables, float4* d_tabl
 // *bad_input is set when a coordinate is NaN / infinite (nothing is splatted then).
 cudaError_t rm_launch_voxelize_points(const float* d_xyz, long long n, int res, int ks, int* d_bb, uint8_t* d_vox,
                                       int* bad_input, cudaStream_t stream);
+
+// ---- wavefront path (rm_wave.cuh, rm_render_wave.cu), RM_OPT_KERNEL = 3 ----
+struct RmWaveScratch {  // HBM scratch of one chunk of items, owned by the context
+  void* d_rec = nullptr;    // (reflectIter + 1) x cap records of 64 B
+  void* d_refl = nullptr;   // cap float4
+  void* d_pxy = nullptr;    // cap float2
+  void* d_jobs = nullptr;   // job_cap jobs of 64 B
+  unsigned* d_ctr = nullptr;  // [0] jobs appended, [1] queue head of the trace kernel
+  unsigned cap = 0, job_cap = 0;
+  int levels = 0;
+};
+void rm_wave_free(RmWaveScratch* w);
+// can the wavefront path render these options? (reflectIter < 8, numLights <= 4; otherwise use the fused kernel)
+int rm_wave_supports(const RmOpts& opts);
+// RenderImage-equivalent for `passes` fusable passes, same contract as rm_launch_render_fast; the items are
+// processed in chunks of at most chunk_items. *launches is incremented by the number of kernels launched.
+cudaError_t rm_launch_render_wave(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
+                                  const float4* d_tables, const float* times, const float* blend, int passes,
+                                  float4* d_colour, float4* d_accum, RmCounters* d_counters, RmWaveScratch* w,
+                                  int num_sms, unsigned chunk_items, int* launches, cudaStream_t stream);

@@ -483,6 +483,117 @@ RM_ST_INLINE void sphere_trace(Scene& s, const Vol& V, float3 ro, float3 rd, Ise
   else r.normal = j.g < 1e5f ? f3(0.0f, 1.0f, 0.0f) : -rd;
 }
 
+// ---- the same trace, one distanceToScene evaluation at a time -------------------------------------
+// For the persistent trace kernel of the wavefront path (rm_render_wave.cu): the lanes of a warp
+// run DIFFERENT rays there and must meet once per evaluation, so the loop of sphere_trace is lifted
+// into a state + a step function. trace_begin / trace_step / trace_finish / trace_surface are
+// sphere_trace cut at its loop; tests/hostsim runs them (via rm_wave.cuh) against the oracle.
+struct TraceSetup {  // per-ray constants, computed where the ray is created (coherently)
+  float3 delta;
+  float invS, inv_step, tin, tout;
+};
+
+template <bool kCount>
+RM_DEV TraceSetup trace_setup(float3 ro, float3 rd, float maxDist) {
+  const RmOpts& o = g_opts;
+  TraceSetup t;
+  t.delta = march_delta(o, rd, o.maxVoxelIter, t.invS);
+  t.inv_step = kCount ? 0.0f : 1.01f / len3(t.delta * o.voxelBounds2);
+  t.tin = -3.0e38f;
+  t.tout = 3.0e38f;
+  if (!kCount) march_window(o, ro, rd, maxDist, t.tin, t.tout);
+  return t;
+}
+
+struct TraceState {
+  float3 ro, rd, pos;
+  TraceSetup c;
+  float maxDist, dist;
+  int maxSteps;
+  bool wantSurface, cut;
+  JobResult j;
+};
+
+RM_DEV void trace_begin(TraceState& t, float3 ro, float3 rd, const TraceSetup& c, float maxDist, int maxSteps, bool wantSurface) {
+  t.ro = ro; t.rd = rd; t.pos = ro; t.c = c;
+  t.maxDist = maxDist; t.dist = g_opts.startDist; t.maxSteps = maxSteps;
+  t.wantSurface = wantSurface; t.cut = false;
+  t.j.g = 0.0f; t.j.dist = 0.0f; t.j.hit = false; t.j.closer = false; t.j.p = f3s(0.0f);
+}
+
+// One iteration of the loop of sphere_trace. Returns true when the loop has ended.
+template <bool kCount, class Vol>
+RM_DEV bool trace_step(Scene& s, const Vol& V, TraceState& t) {
+  const RmOpts& o = g_opts;
+  if (--t.maxSteps < 0) return true;
+  if (kCount) s.w.outer++;
+  RM_STAT_EVENT(t.wantSurface ? 8 : 9);
+  t.pos = t.ro + t.rd * t.dist;
+  const float g = t.pos.y + o.groundY;
+  if (!kCount && (t.dist > t.c.tout || t.c.tin - t.dist > g * 1.0001f + 1e-3f || g <= 0.0f)) {
+    RM_STAT_EVENT(12);
+    t.j.g = g;
+    t.j.dist = g < 1e5f ? g : 1e5f;
+    t.j.hit = false;
+    t.j.closer = false;
+    t.cut = false;
+    if (t.dist > t.c.tout && t.rd.y >= 0.0f && g > o.eps && g < 1e5f && t.maxSteps < 65536 &&
+        (float)(t.maxSteps + 1) * g * 0.99f >= t.maxDist - t.dist) {
+      RM_STAT_EVENT(17);
+      t.dist = t.maxDist;
+      return true;
+    }
+  } else {
+    int limit = o.maxVoxelIter;
+    if (!kCount) {
+      float reach = g;
+      if (!t.wantSurface) reach = fminf(reach, fmaxf(t.maxDist - t.dist, o.eps));
+      const float k = (reach + o.voxelSize) * t.c.inv_step;
+      t.cut = k < (float)(limit - 2);
+      if (t.cut) limit = f2i_sat(k) + 2;
+    }
+    t.j = scene_distance<kCount>(s, V, t.pos, t.rd, t.c.delta, limit, t.c.invS, false);
+  }
+  if (fabsf(t.j.dist) <= o.eps || t.dist >= t.maxDist) return true;
+  t.dist += t.j.dist;
+  return false;
+}
+
+// After the loop: the repeated full call of the voxel-normal quirk, and the miss bookkeeping.
+// Returns true on a miss; t.dist / t.pos are then TIsec.distance (1000) / TIsec.pos.
+template <bool kCount, class Vol>
+RM_DEV bool trace_finish(Scene& s, const Vol& V, TraceState& t) {
+  const RmOpts& o = g_opts;
+  if (!kCount && t.wantSurface && t.cut && !t.j.hit) {
+    RM_STAT_EVENT(10);
+    t.j = scene_distance<kCount>(s, V, t.pos, t.rd, t.c.delta, o.maxVoxelIter, t.c.invS, false);
+  }
+  const bool miss = t.dist >= t.maxDist;
+  if (miss) {
+    t.pos = t.ro + t.rd * t.dist;
+    t.dist = 1000.0f;
+  }
+  return miss;
+}
+
+// objectID and normal of a finished (non-smooth) surface trace, from what its last evaluation found
+template <class Vol>
+RM_DEV void trace_surface(const Vol& V, float3 rd, bool miss, bool hit, bool closer, float3 jp, float jg, int& objectID, float3& normal) {
+  const RmOpts& o = g_opts;
+  objectID = -1;
+  const int x = f2i_sat(jp.x * (float)o.rx), y = f2i_sat(jp.y * (float)o.ry), z = f2i_sat(jp.z * (float)o.rz);
+  if (!miss) {
+    if (closer) {
+      const int v = V.value(o, x, y, z);
+      objectID = v < 168 ? (v < 84 ? 1 : 2) : 3;
+    } else {
+      objectID = f2i_sat(jg < 1e5f ? jg : -1.0f);
+    }
+  }
+  if (hit) normal = normal_6tap(V, o, x, y, z);
+  else normal = jg < 1e5f ? f3(0.0f, 1.0f, 0.0f) : -rd;
+}
+
 RM_DEV float3 sky(const RmOpts& o, float3 d) { return lerp3(o.sky1, o.sky2, d.y * 0.5f + 0.5f); }  // :259-261
 
 // renderer.cl:263-269

@@ -25,7 +25,12 @@ namespace wave {
 
 using namespace plain;
 
-enum : unsigned { kLitMask = 0xfu, kValid = 1u << 8, kSurface = 1u << 9 };
+enum : unsigned {
+  kLitMask = 0xfu, kValid = 1u << 8, kSurface = 1u << 9,
+  // a bounce record as the trace kernel leaves it: nrm = sample position of the last hit, ao = ground
+  // distance of the last evaluation, and these bits; resolve_record turns that into normal / objectID
+  kRaw = 1u << 10, kRawHit = 1u << 11, kRawCloser = 1u << 12, kRawMiss = 1u << 13
+};
 constexpr int kMaxLevels = 8;       // primary + up to 7 bounces (TRenderOpts.reflectIter beyond that: fused kernel)
 constexpr int kBounceKind = 4;      // job kinds 0..3 = shadow ray of light i
 
@@ -37,9 +42,11 @@ struct WaveRec {  // 64 bytes: the ray of one level of one item and what it foun
                                // bit i: the shadow ray of light i reached the light
 };
 
-struct WaveJob {  // 32 bytes
+struct WaveJob {  // 64 bytes
   float3 org;  float maxDist;
   float3 dir;  unsigned info;  // item | level << 24 | kind << 27
+  TraceSetup c;                // march step, skip scale, march window: computed where the ray is created
+  float pad;
 };
 
 struct WaveBuf {
@@ -61,11 +68,14 @@ inline void wave_atomic_or(unsigned* p, unsigned v) { __atomic_fetch_or(p, v, __
 
 RM_DEV WaveRec& rec_at(const WaveBuf& B, int level, unsigned it) { return B.rec[(size_t)level * B.cap + it]; }
 
+template <bool kCount>
 RM_DEV void push_job(const WaveBuf& B, float3 org, float3 dir, float maxDist, unsigned it, int level, int kind) {
   const unsigned k = wave_atomic_inc(B.njobs);
   if (k >= B.job_cap) return;  // cannot happen: the launcher sizes the queue for (numLights + 1) jobs per item
   WaveJob j;
   j.org = org; j.maxDist = maxDist; j.dir = dir;
+  j.c = trace_setup<kCount>(org, dir, maxDist);
+  j.pad = 0.0f;
   j.info = it | ((unsigned)level << 24) | ((unsigned)kind << 27);
   B.jobs[k] = j;
 }
@@ -152,6 +162,19 @@ RM_DEV PixelState pixel_state_of(const WaveBuf& B, unsigned it) {
   return st;
 }
 
+// normal and objectID of a bounce record the trace kernel has filled (done once, by the first stage that reads it)
+template <class Vol>
+RM_DEV void resolve_record(WaveRec& r, const Vol& V) {
+  if (!(r.flags & kRaw)) return;
+  int obj;
+  float3 n;
+  trace_surface(V, r.dir, (r.flags & kRawMiss) != 0, (r.flags & kRawHit) != 0, (r.flags & kRawCloser) != 0, r.nrm, r.ao, obj, n);
+  r.obj = obj;
+  r.nrm = n;
+  r.ao = 0.0f;
+  r.flags &= ~(kRaw | kRawHit | kRawCloser | kRawMiss);
+}
+
 // does record L of this item hold a surface that is to be shaded?
 RM_DEV bool is_surface(const WaveRec& r, int level) {
   if (!(r.flags & kValid)) return false;
@@ -164,6 +187,7 @@ RM_DEV void wave_prepare(const WaveBuf& B, unsigned it, Scene& s, const Vol& V, 
   const RmOpts& o = g_opts;
   WaveRec& r = rec_at(B, level, it);
   if (level + 1 < kMaxLevels) rec_at(B, level + 1, it).flags = 0;
+  resolve_record(r, V);
   if (!is_surface(r, level)) return;
   const PixelState st = pixel_state_of(B, it);
   const RmMaterial& m = o.mat[mat_index(r.obj)];
@@ -173,7 +197,7 @@ RM_DEV void wave_prepare(const WaveBuf& B, unsigned it, Scene& s, const Vol& V, 
   r.flags = flags;
   for (int i = 0; i < o.numLights; ++i) {
     const LightTerms t = light_terms<kCount>(s, st, r.dir, r.pos, m, r.nrm, i);
-    if (t.on && t.traced) push_job(B, r.pos + t.ldir * o.shadowBias, t.ldir, t.lmax, it, level, i);
+    if (t.on && t.traced) push_job<kCount>(B, r.pos + t.ldir * o.shadowBias, t.ldir, t.lmax, it, level, i);
   }
   // the next bounce (sceneColor :421-432): from the primary surface when it reflects at all, from a
   // bounce surface while the budget lasts and the surface is not (nearly) matt
@@ -183,36 +207,48 @@ RM_DEV void wave_prepare(const WaveBuf& B, unsigned it, Scene& s, const Vol& V, 
     const float3 bo = r.pos + bd * 0.0075f;
     WaveRec& nx = rec_at(B, level + 1, it);
     nx.dir = bd; nx.org = bo; nx.flags = kValid; nx.ao = 0.0f;
-    push_job(B, bo, bd, o.maxDist, it, level + 1, kBounceKind);
+    push_job<kCount>(B, bo, bd, o.maxDist, it, level + 1, kBounceKind);
   }
 }
 
-// Stage 3: one job.
+// Stage 3: one job = trace_begin, trace_step until done, job_end. (The persistent kernel runs the
+// three pieces itself, one step per trip of its loop.)
+RM_DEV void job_begin(const WaveJob& j, TraceState& t) {
+  const RmOpts& o = g_opts;
+  const bool bounce = (j.info >> 27) == (unsigned)kBounceKind;
+  trace_begin(t, j.org, j.dir, j.c, j.maxDist, bounce ? o.maxIter : o.shadowIter, bounce);
+}
+
+template <bool kCount, class Vol>
+RM_DEV void job_end(const WaveBuf& B, unsigned info, Scene& s, const Vol& V, TraceState& t) {
+  const unsigned it = info & 0xffffffu;
+  const int level = (int)((info >> 24) & 7u), kind = (int)(info >> 27);
+  const bool miss = trace_finish<kCount>(s, V, t);
+  WaveRec& w = rec_at(B, level, it);
+  if (kind == kBounceKind) {
+    w.pos = t.pos; w.dist = t.dist; w.nrm = t.j.p; w.ao = t.j.g; w.obj = -1;
+    w.flags = kValid | kRaw | (t.j.hit ? kRawHit : 0u) | (t.j.closer ? kRawCloser : 0u) | (miss ? kRawMiss : 0u);
+  } else if (!(t.dist < t.maxDist)) {
+    wave_atomic_or(&w.flags, 1u << kind);  // shadow() :292-301: the ray reached the light
+  }
+}
+
 template <bool kCount, class Vol>
 RM_DEV void wave_trace(const WaveBuf& B, const WaveJob& j, Scene& s, const Vol& V) {
-  const RmOpts& o = g_opts;
-  const unsigned it = j.info & 0xffffffu;
-  const int level = (int)((j.info >> 24) & 7u), kind = (int)(j.info >> 27);
-  Isec r;
-  RM_STAT_LEVEL(kind == kBounceKind ? level - 1 : level);
-  if (kind == kBounceKind) {
-    RM_STAT_SITE(level * 16);
-    sphere_trace<kCount>(s, V, j.org, j.dir, r, j.maxDist, o.maxIter, false, true);
-    WaveRec& w = rec_at(B, level, it);
-    w.pos = r.pos; w.dist = r.distance; w.nrm = r.normal; w.obj = r.objectID;
-  } else {
-    RM_STAT_SITE(level * 16 + 1 + kind);
-    sphere_trace<kCount>(s, V, j.org, j.dir, r, j.maxDist, o.shadowIter, false, false);
-    if (!(r.distance < j.maxDist)) wave_atomic_or(&rec_at(B, level, it).flags, 1u << kind);  // shadow() :292-301
-  }
+  TraceState t;
+  RM_STAT_SITE((int)((j.info >> 24) & 7u) * 16 + ((j.info >> 27) == (unsigned)kBounceKind ? 0 : 1 + (int)(j.info >> 27)));
+  job_begin(j, t);
+  while (!trace_step<kCount>(s, V, t)) {}
+  job_end<kCount>(B, j.info, s, V, t);
 }
 
 // Stage 4 for level L >= 1 (basicSceneColor :383-405 after its trace).
-template <bool kCount>
-RM_DEV void wave_finish(const WaveBuf& B, unsigned it, const Scene& s, int level) {
+template <bool kCount, class Vol>
+RM_DEV void wave_finish(const WaveBuf& B, unsigned it, const Scene& s, const Vol& V, int level) {
   const RmOpts& o = g_opts;
-  const WaveRec& r = rec_at(B, level, it);
+  WaveRec& r = rec_at(B, level, it);
   if (!(r.flags & kValid)) return;
+  resolve_record(r, V);  // (a no-op when wave_prepare(level) has run, i.e. always but for a level beyond the last prepare)
   const PixelState st = pixel_state_of(B, it);
   float3 col;
   if (r.obj < 0) {

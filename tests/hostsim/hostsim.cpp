@@ -239,8 +239,8 @@ void sim_render_pixels_wave(const uint8_t* vox, const float* mc, const void* opt
   else { SIM_STAGE(wave::wave_primary<true>(B, (unsigned)it, s, V, ids ? ids[it] : it)) }
   for (int L = 0; L <= lmax; ++L) {
     njobs = 0;
-    if (mode == 0) { SIM_STAGE(if (L >= 2) wave::wave_finish<false>(B, (unsigned)it, s, L - 1); wave::wave_prepare<false>(B, (unsigned)it, s, V, L)) }
-    else { SIM_STAGE(if (L >= 2) wave::wave_finish<true>(B, (unsigned)it, s, L - 1); wave::wave_prepare<true>(B, (unsigned)it, s, V, L)) }
+    if (mode == 0) { SIM_STAGE(if (L >= 2) wave::wave_finish<false>(B, (unsigned)it, s, V, L - 1); wave::wave_prepare<false>(B, (unsigned)it, s, V, L)) }
+    else { SIM_STAGE(if (L >= 2) wave::wave_finish<true>(B, (unsigned)it, s, V, L - 1); wave::wave_prepare<true>(B, (unsigned)it, s, V, L)) }
     const int nj = (int)std::min<size_t>(njobs, jobs.size());
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : cs, ct, co)
     for (int k = 0; k < nj; ++k) {
@@ -255,8 +255,8 @@ void sim_render_pixels_wave(const uint8_t* vox, const float* mc, const void* opt
     plain::Scene s(vox, table);
     const int id = ids ? ids[it] : it;
     float3 c;
-    if (mode == 0) { if (lmax >= 1) wave::wave_finish<false>(B, (unsigned)it, s, lmax); c = wave::wave_final<false>(B, (unsigned)it, s); }
-    else { if (lmax >= 1) wave::wave_finish<true>(B, (unsigned)it, s, lmax); c = wave::wave_final<true>(B, (unsigned)it, s); }
+    if (mode == 0) { if (lmax >= 1) wave::wave_finish<false>(B, (unsigned)it, s, V, lmax); c = wave::wave_final<false>(B, (unsigned)it, s); }
+    else { if (lmax >= 1) wave::wave_finish<true>(B, (unsigned)it, s, V, lmax); c = wave::wave_final<true>(B, (unsigned)it, s); }
     float* px = pixels + 4 * (size_t)id;
     const float3 m = lerp3(make_float3(px[0], px[1], px[2]), c, o.frameBlend);
     px[0] = m.x; px[1] = m.y; px[2] = m.z; px[3] = 1.0f;

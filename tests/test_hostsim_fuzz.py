@@ -85,8 +85,9 @@ def test_random_options_production_routine_is_bit_identical(checkers, seed):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", [0, 3], ids=["fast", "wave"])
 @pytest.mark.parametrize("seed", range(0, 160, 5))
-def test_random_options_on_the_gpu(checkers, gpu_renderer, seed):
+def test_random_options_on_the_gpu(checkers, gpu_renderer, seed, kernel):
     """The same randomised blobs through the C ABI on the GPU: production and counting kernels
     agree bit for bit with each other, the work counters equal the oracle's, and the accumulator is
     within 2e-5 relative of it wherever it is finite (exp / exp2 / pow differ in the last ulp
@@ -101,7 +102,8 @@ def test_random_options_on_the_gpu(checkers, gpu_renderer, seed):
     mcs = [generate_scatter_offsets(0x4000, 77 + seed + i) for i in range(2)]
     ref, ref_cnt = orc.render_frame(vol, mcs, opts, W, H)
     r = gpu_renderer
-    r.set_option(2, 0)
+    r.set_option(2, kernel)
+    r.set_option(8, 1024 if seed % 2 else 1 << 21)  # wavefront path: several chunks per frame, or one
     r.set_tile_shard(0, 1, 32, 32)
     out = {}
     for count in (True, False):
@@ -115,6 +117,7 @@ def test_random_options_on_the_gpu(checkers, gpu_renderer, seed):
         if count:
             assert [st["steps"], st["taps"], st["outer_iters"]] == [int(x) for x in ref_cnt]
     r.count_work(False)
+    r.set_option(2, 0)
     a, b = out[True].view(np.uint32), out[False].view(np.uint32)
     assert ((a == b) | (np.isnan(out[True]) & np.isnan(out[False]))).all(), "production and counting kernels differ"
     px = out[False].astype(np.float64)
