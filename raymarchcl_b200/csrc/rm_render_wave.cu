@@ -101,10 +101,14 @@ k_wave_prepare(const __grid_constant__ RmShard sh, const __grid_constant__ WaveP
 
 // Persistent trace kernel. The grid is a fixed number of blocks; a warp takes batches of kBatch
 // consecutive jobs from the queue head (one atomic per batch) and hands them to its lanes as they
-// fall idle. One trip of the loop = at most one distanceToScene evaluation per lane (trace_step), so
+// fall idle. One trip of the loop = at most one full distanceToScene evaluation per lane (trace_full), so
 // the 32 lanes -- each on its own ray, at its own iteration -- meet once per evaluation; a lane whose
 // ray has ended writes its result and takes the next job on the following trip.
 constexpr unsigned kBatch = 128;
+#ifndef RM_WAVE_CHEAP_PER_TRIP
+#define RM_WAVE_CHEAP_PER_TRIP 8  // measured on B200 (C2, 16 M-item chunks): 2 / 4 / 8 / unlimited = 60.1 / 57.4 / 56.2 / 57.0 ms
+#endif
+constexpr int kCheapPerTrip = RM_WAVE_CHEAP_PER_TRIP;  // ground-only evaluations a lane may run per trip
 
 template <bool kCount>
 __global__ void __launch_bounds__(kBlock)
@@ -141,7 +145,14 @@ k_wave_trace(const __grid_constant__ wave::WaveBuf B, unsigned* __restrict__ hea
       if (dry) break;
       continue;
     }
-    if (have && plain::trace_step<kCount>(s, V, t)) {
+    // each lane runs through its ground-only evaluations, then the lanes that need a full
+    // distanceToScene call make it together
+    bool done = false;
+    int st = plain::kTraceDone;
+    if (have) st = plain::trace_run_cheap<kCount>(s, t, kCheapPerTrip);
+    if (have && st == plain::kTraceDone) done = true;
+    if (have && st == plain::kTraceNeedsFull) done = plain::trace_full<kCount>(s, V, t);
+    if (have && done) {
       wave::job_end<kCount>(B, info, s, V, t);
       have = false;
     }

@@ -521,16 +521,23 @@ RM_DEV void trace_begin(TraceState& t, float3 ro, float3 rd, const TraceSetup& c
   t.j.g = 0.0f; t.j.dist = 0.0f; t.j.hit = false; t.j.closer = false; t.j.p = f3s(0.0f);
 }
 
-// One iteration of the loop of sphere_trace. Returns true when the loop has ended.
-template <bool kCount, class Vol>
-RM_DEV bool trace_step(Scene& s, const Vol& V, TraceState& t) {
+// The loop of sphere_trace in two halves, so that the lanes of the persistent trace kernel meet at
+// the expensive one: trace_run_cheap runs this ray's ground-only evaluations (a few instructions
+// each) until the ray ends (returns true) or its next evaluation has to be a full distanceToScene
+// call (returns false, t.pos set); trace_full makes that call and returns true when the ray ends.
+// Together they are exactly one or more iterations of the loop of sphere_trace.
+enum { kTraceNeedsFull = 0, kTraceDone = 1, kTraceMoreCheap = 2 };
+template <bool kCount>
+RM_DEV int trace_run_cheap(Scene& s, TraceState& t, int budget) {
   const RmOpts& o = g_opts;
-  if (--t.maxSteps < 0) return true;
-  if (kCount) s.w.outer++;
-  RM_STAT_EVENT(t.wantSurface ? 8 : 9);
-  t.pos = t.ro + t.rd * t.dist;
-  const float g = t.pos.y + o.groundY;
-  if (!kCount && (t.dist > t.c.tout || t.c.tin - t.dist > g * 1.0001f + 1e-3f || g <= 0.0f)) {
+  for (;; --budget) {
+    if (budget <= 0) return kTraceMoreCheap;  // the lanes of a warp wait for the longest run: keep runs short
+    if (--t.maxSteps < 0) return kTraceDone;
+    if (kCount) s.w.outer++;
+    RM_STAT_EVENT(t.wantSurface ? 8 : 9);
+    t.pos = t.ro + t.rd * t.dist;
+    const float g = t.pos.y + o.groundY;
+    if (kCount || !(t.dist > t.c.tout || t.c.tin - t.dist > g * 1.0001f + 1e-3f || g <= 0.0f)) return kTraceNeedsFull;
     RM_STAT_EVENT(12);
     t.j.g = g;
     t.j.dist = g < 1e5f ? g : 1e5f;
@@ -541,19 +548,25 @@ RM_DEV bool trace_step(Scene& s, const Vol& V, TraceState& t) {
         (float)(t.maxSteps + 1) * g * 0.99f >= t.maxDist - t.dist) {
       RM_STAT_EVENT(17);
       t.dist = t.maxDist;
-      return true;
+      return kTraceDone;
     }
-  } else {
-    int limit = o.maxVoxelIter;
-    if (!kCount) {
-      float reach = g;
-      if (!t.wantSurface) reach = fminf(reach, fmaxf(t.maxDist - t.dist, o.eps));
-      const float k = (reach + o.voxelSize) * t.c.inv_step;
-      t.cut = k < (float)(limit - 2);
-      if (t.cut) limit = f2i_sat(k) + 2;
-    }
-    t.j = scene_distance<kCount>(s, V, t.pos, t.rd, t.c.delta, limit, t.c.invS, false);
+    if (fabsf(t.j.dist) <= o.eps || t.dist >= t.maxDist) return kTraceDone;
+    t.dist += t.j.dist;
   }
+}
+
+template <bool kCount, class Vol>
+RM_DEV bool trace_full(Scene& s, const Vol& V, TraceState& t) {
+  const RmOpts& o = g_opts;
+  int limit = o.maxVoxelIter;
+  if (!kCount) {
+    float reach = t.pos.y + o.groundY;
+    if (!t.wantSurface) reach = fminf(reach, fmaxf(t.maxDist - t.dist, o.eps));
+    const float k = (reach + o.voxelSize) * t.c.inv_step;
+    t.cut = k < (float)(limit - 2);
+    if (t.cut) limit = f2i_sat(k) + 2;
+  }
+  t.j = scene_distance<kCount>(s, V, t.pos, t.rd, t.c.delta, limit, t.c.invS, false);
   if (fabsf(t.j.dist) <= o.eps || t.dist >= t.maxDist) return true;
   t.dist += t.j.dist;
   return false;
