@@ -80,7 +80,9 @@ typedef enum rm_option {
   RM_OPT_FUSE_LIMIT = 6,   /* max passes rendered by one launch (1..32) */
   RM_OPT_TRIP_LIMIT = 7,   /* watchdog of kernel 2: scheduling trips a warp may take per launch before
                               the launch is abandoned with RM_ERR_CUDA (default 2^28) */
-  RM_OPT_WAVE_CHUNK = 8    /* kernel 3: (pixel, pass) items per chunk of the pipeline (1024..2^24, default 2^21) */
+  RM_OPT_WAVE_CHUNK = 8,   /* kernel 3: (pixel, pass) items per chunk of the pipeline (1024..2^24, default 2^24) */
+  RM_OPT_WAVE_REFILL = 9   /* kernel 3: the trace kernel hands new rays to idle lanes once this many lanes of a
+                              warp are idle (1 = at once ... 32 = the warp starts 32 rays together) */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */

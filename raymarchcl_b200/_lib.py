@@ -23,6 +23,7 @@ RM_OPT_CELL_SHIFT = 3
 RM_OPT_FUSE_LIMIT = 6
 RM_OPT_TRIP_LIMIT = 7
 RM_OPT_WAVE_CHUNK = 8
+RM_OPT_WAVE_REFILL = 9
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [

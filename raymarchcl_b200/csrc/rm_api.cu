@@ -65,7 +65,8 @@ struct rm_ctx {
   unsigned trip_limit = 1u << 28;
   int warp_blocks[2] = {0, 0};            // resident blocks per SM of the warp kernel [plain, counting]
   RmWaveScratch wave;                     // scratch of the wavefront path (kernel 3)
-  unsigned wave_chunk = 1u << 21;         // items per chunk of the wavefront path
+  unsigned wave_chunk = 1u << 24;         // items per chunk of the wavefront path
+  int wave_refill = 16;                   // its trace kernel refills when this many lanes of a warp are idle (B200, C2: 1 / 16 / 28 / 32 = 56.3 / 54.4 / 55.2 / 54.6 ms)
   int cell_shift_opt = 0;           // 0 = auto
   int fuse_limit = RM_MAX_FUSED_PASSES;
 
@@ -297,7 +298,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
       } else if (c->kernel_kind == 3 && rm_wave_supports(passes[i])) {
         int launched = 0;
         e = rm_launch_render_wave(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
-                                  c->d_colour, c->d_accum, cnt, &c->wave, c->num_sms, c->wave_chunk, &launched, c->stream);
+                                  c->d_colour, c->d_accum, cnt, &c->wave, c->num_sms, c->wave_chunk, c->wave_refill, &launched, c->stream);
         c->stats.kernel_launches += launched - (m > 1 ? 2 : 1);  // (the common bookkeeping below adds that much)
       } else {
         e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
@@ -832,6 +833,10 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
     case RM_OPT_WAVE_CHUNK:
       if (value < 1024 || value > (1ll << 24)) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_WAVE_CHUNK: 1024..2^24 items");
       c->wave_chunk = (unsigned)value;
+      return RM_OK;
+    case RM_OPT_WAVE_REFILL:
+      if (value < 1 || value > 32) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_WAVE_REFILL: 1..32 idle lanes");
+      c->wave_refill = (int)value;
       return RM_OK;
     case RM_OPT_TRIP_LIMIT:
       if (value < 1 || value > 0xffffffffLL) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_TRIP_LIMIT: 1..2^32-1");

@@ -99,8 +99,9 @@ void rm_wave_free(RmWaveScratch* w);
 // can the wavefront path render these options? (reflectIter < 8, numLights <= 4; otherwise use the fused kernel)
 int rm_wave_supports(const RmOpts& opts);
 // RenderImage-equivalent for `passes` fusable passes, same contract as rm_launch_render_fast; the items are
-// processed in chunks of at most chunk_items. *launches is incremented by the number of kernels launched.
+// processed in chunks of at most chunk_items; refill_min_idle (1..32) is the trace kernel's refill policy.
+// *launches is incremented by the number of kernels launched.
 cudaError_t rm_launch_render_wave(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                   const float4* d_tables, const float* times, const float* blend, int passes,
                                   float4* d_colour, float4* d_accum, RmCounters* d_counters, RmWaveScratch* w,
-                                  int num_sms, unsigned chunk_items, int* launches, cudaStream_t stream);
+                                  int num_sms, unsigned chunk_items, int refill_min_idle, int* launches, cudaStream_t stream);

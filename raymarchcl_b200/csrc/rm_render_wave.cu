@@ -112,7 +112,7 @@ constexpr int kCheapPerTrip = RM_WAVE_CHEAP_PER_TRIP;  // ground-only evaluation
 
 template <bool kCount>
 __global__ void __launch_bounds__(kBlock)
-k_wave_trace(const __grid_constant__ wave::WaveBuf B, unsigned* __restrict__ head, RmCounters* counters) {
+k_wave_trace(const __grid_constant__ wave::WaveBuf B, unsigned* __restrict__ head, RmCounters* counters, int min_idle) {
   const unsigned kFull = 0xffffffffu;
   plain::Scene s(plain::g_accel.vox, nullptr);
   const plain::BrickVolume V{};
@@ -123,7 +123,12 @@ k_wave_trace(const __grid_constant__ wave::WaveBuf B, unsigned* __restrict__ hea
   bool have = false, dry = false;   // dry: the queue head has passed the end (warp-uniform)
   unsigned wnext = 0, wend = 0;     // the warp's current batch [wnext, wend) (warp-uniform)
   for (;;) {
-    const unsigned want = __ballot_sync(kFull, !have);
+    // Refill policy: idle lanes take new rays only when at least min_idle lanes are idle. 1 = a lane
+    // refills as soon as its ray ends (best balance, but the lanes of a warp drift to unrelated rays
+    // and iterations); 32 = the warp starts 32 consecutive rays of the queue together and finishes
+    // them together, which keeps neighbouring rays -- same pixels, different passes -- in step.
+    unsigned want = __ballot_sync(kFull, !have);
+    if ((int)__popc(want) < min_idle) want = 0;
     if (want && wnext >= wend && !dry) {
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(head, kBatch);
@@ -131,7 +136,7 @@ k_wave_trace(const __grid_constant__ wave::WaveBuf B, unsigned* __restrict__ hea
       if (base >= n) { dry = true; }
       else { wnext = base; wend = min(base + kBatch, n); }
     }
-    if (!have && wnext < wend) {
+    if (!have && want && wnext < wend) {
       const unsigned k = wnext + __popc(want & ((1u << lane) - 1u));
       if (k < wend) {
         const wave::WaveJob j = B.jobs[k];
@@ -213,7 +218,7 @@ int rm_wave_supports(const RmOpts& opts) { return opts.reflectIter < wave::kMaxL
 cudaError_t rm_launch_render_wave(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                   const float4* d_tables, const float* times, const float* blend, int passes,
                                   float4* d_colour, float4* d_accum, RmCounters* d_counters, RmWaveScratch* w,
-                                  int num_sms, unsigned chunk_items, int* launches, cudaStream_t stream) {
+                                  int num_sms, unsigned chunk_items, int refill_min_idle, int* launches, cudaStream_t stream) {
   if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
   if (passes > RM_MAX_FUSED_PASSES || !rm_wave_supports(opts)) return cudaErrorInvalidValue;
   const long long total = (long long)passes * shard.slots;
@@ -256,10 +261,10 @@ cudaError_t rm_launch_render_wave(const RmOpts& opts, const RmShard& shard, cons
       if ((e = cudaMemsetAsync(w->d_ctr, 0, 2 * sizeof(unsigned), stream)) != cudaSuccess) return e;
       if (d_counters) {
         k_wave_prepare<true><<<blocks, kBlock, 0, stream>>>(shard, P, B, L);
-        k_wave_trace<true><<<trace_blocks, kBlock, 0, stream>>>(B, head, d_counters);
+        k_wave_trace<true><<<trace_blocks, kBlock, 0, stream>>>(B, head, d_counters, refill_min_idle);
       } else {
         k_wave_prepare<false><<<blocks, kBlock, 0, stream>>>(shard, P, B, L);
-        k_wave_trace<false><<<trace_blocks, kBlock, 0, stream>>>(B, head, d_counters);
+        k_wave_trace<false><<<trace_blocks, kBlock, 0, stream>>>(B, head, d_counters, refill_min_idle);
       }
       *launches += 2;
     }
