@@ -59,3 +59,20 @@ def test_production_march_elides_most_fetches(sim):
     sim.render_frame(vol, mcs, opts, kw["width"], kw["height"], mode="production")
     st = sim.stats()
     assert 0 < st["lookups"] < int(cnt[0]) // 2  # the production march looks at far fewer samples than the reference fetches
+
+
+@pytest.mark.parametrize("vres", [(96, 40, 130), (33, 70, 45)], ids=str)
+@pytest.mark.parametrize("mode", ["production", "counting", "wave"])
+def test_ragged_grids(sim, orc, vres, mode):
+    """Extents that are neither equal nor multiples of the brick / macro-cell edge."""
+    from raymarchcl_b200 import compute_eyepos, generate_scatter_offsets, make_gyroid_volume, make_render_option_buffers
+    vol = make_gyroid_volume(vres)
+    w, h = 48, 32
+    opts = make_render_option_buffers(2, dict(width=w, height=h, vres=list(vres), iter=2, mat="metal",
+                                              eyepos=compute_eyepos(120.0, 2.0, 0.5), targetpos=[0, -0.3, 0]))
+    mcs = [generate_scatter_offsets(0x4000, 5 + i) for i in range(2)]
+    ref, ref_cnt = orc.render_frame(vol, mcs, opts, w, h)
+    px, cnt = sim.render_frame(vol, mcs, opts, w, h, mode=mode, cell_shift=3 if mode == "wave" else 2)
+    assert np.array_equal(px.view(np.uint32), ref.view(np.uint32))
+    if mode == "counting":
+        assert np.array_equal(cnt, ref_cnt)

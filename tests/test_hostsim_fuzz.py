@@ -54,8 +54,16 @@ def _random_fields(rng: np.random.Generator, vres: int):
     return f
 
 
+def _noise(r, solid):
+    """Random bytes: the worst case for the bit-bricks / distance map (solid voxels everywhere or almost nowhere)."""
+    rng = np.random.default_rng(r)
+    v = rng.integers(0, 256, size=(r, r, r), dtype=np.uint8)
+    return np.where(rng.random((r, r, r)) < solid, v, 0).astype(np.uint8)
+
+
 VOLUMES = {"gyroid": lambda r: make_gyroid_volume(r), "terrain": lambda r: make_terrain(r),
-           "blob": lambda r: make_blob_volume(r, ks=1)}
+           "blob": lambda r: make_blob_volume(r, ks=1),
+           "noise_dense": lambda r: _noise(r, 0.3), "noise_sparse": lambda r: _noise(r, 0.004)}
 
 
 @pytest.fixture(scope="module")
