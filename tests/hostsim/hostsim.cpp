@@ -20,18 +20,21 @@ struct SimStats {
 static thread_local SimStats t_stats;
 // per call site cost model of one pixel-sample (instruction estimates: cheap evaluation 15, full
 // distanceToScene call 150, march lookup 50, skipped sample 3)
+// per pixel-sample log of the full distanceToScene evaluations: (call site << 8 | table lookups), in order
+static thread_local unsigned short t_eval_log[256];
+static thread_local int t_eval_n;
 static thread_local float t_site_cost[64];
 static thread_local int t_site, t_level;
 #define RM_STAT_SITE(id) (t_site = (id) & 63)
 #define RM_STAT_LEVEL(l) (t_level = (l))
 #define RM_STAT_LEVEL_GET() t_level
-#define RM_STAT_LOOKUP() (t_stats.lookups++, t_site_cost[t_site] += 50.0f)
+#define RM_STAT_LOOKUP() (t_stats.lookups++, t_site_cost[t_site] += 50.0f, (t_eval_n > 0 && t_eval_n <= 256 && (t_eval_log[t_eval_n - 1] & 255) < 255) ? (void)++t_eval_log[t_eval_n - 1] : (void)0)
 #define RM_STAT_SKIP(n) (t_stats.skips++, t_stats.skipped_samples += (n), t_stats.hist[stat_bucket(n)]++, t_site_cost[t_site] += 3.0f * (n))
 #define RM_STAT_JUMP(n) (t_stats.jumps++, t_stats.jump_samples += (n))
 #define RM_STAT_SEQ(n) (t_stats.seq_adds += (n))
 #define RM_STAT_MARCH() (t_stats.marches++)
 #define RM_STAT_TRACE() (t_stats.traces++)
-#define RM_STAT_EVENT(id) (t_stats.events[(id)]++, t_site_cost[t_site] += ((id) == 0 ? 150.0f : ((id) == 12 ? 15.0f : 0.0f)))
+#define RM_STAT_EVENT(id) (t_stats.events[(id)]++, t_site_cost[t_site] += ((id) == 0 ? 150.0f : ((id) == 12 ? 15.0f : 0.0f)), ((id) == 0 && t_eval_n < 256) ? (void)(t_eval_log[t_eval_n++] = (unsigned short)(t_site << 8)) : (void)0)
 static inline int stat_bucket(int n) {
   int b = 0;
   while (n > 1 && b < 15) { n >>= 1; ++b; }
@@ -141,6 +144,7 @@ void build_accel(const uint8_t* vox, int rx, int ry, int rz, int iso, int cell_s
 }
 
 float* g_cost_out = nullptr;  // optional: count x 64 floats, per-site cost of every rendered pixel-sample
+unsigned short* g_eval_out = nullptr;  // optional: count x 256 entries, the evaluation log of every pixel-sample (0xffff = end)
 HostAccel g_host_accel;
 const uint8_t* g_accel_vox = nullptr;
 int g_accel_key[5] = {0, 0, 0, -1, -1};
@@ -179,7 +183,7 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
       const int id = ids ? ids[k] : k;
       plain::Scene s(vox, reinterpret_cast<const float4*>(mc));
       std::memset(t_site_cost, 0, sizeof t_site_cost);
-      t_site = 0; t_level = 0;
+      t_site = 0; t_level = 0; t_eval_n = 0;
       float3 c;
       if (mode == 0) c = plain::render_pixel_sample<false>(s, plain::BrickVolume{}, id);
       else if (mode == 1) c = plain::render_pixel_sample<true>(s, plain::BrickVolume{}, id);
@@ -189,6 +193,10 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
       px[0] = m.x; px[1] = m.y; px[2] = m.z; px[3] = 1.0f;
       cs += s.w.steps; ct += s.w.taps; co += s.w.outer;
       if (g_cost_out) std::memcpy(g_cost_out + 64 * (size_t)k, t_site_cost, sizeof t_site_cost);
+      if (g_eval_out) {
+        unsigned short* dst = g_eval_out + 256 * (size_t)k;
+        for (int e = 0; e < 256; ++e) dst[e] = e < t_eval_n ? t_eval_log[e] : (unsigned short)0xffff;
+      }
     }
 #pragma omp critical
     {
@@ -201,6 +209,7 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
 }
 
 void sim_set_cost_buffer(float* p) { g_cost_out = p; }
+void sim_set_eval_buffer(unsigned short* p) { g_eval_out = p; }
 // The wavefront stages of rm_wave.cuh run on the host in the launcher's order (rm_render_wave.cu):
 // primary; per level L: [finish(L-1)], prepare(L), all queued traces; finish(last); final.
 // mode: 0 = production routine, 1 = counting routine.

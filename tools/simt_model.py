@@ -16,9 +16,11 @@ sample. Pixel-samples are then grouped into warps exactly like the fused kernel'
   warp job pool                the jobs of a warp's 32 items per wave, list-scheduled over 32 lanes
   refill, ideal                every lane always busy: 32
 
-"lanes" = total thread cost / total lock-step cost = useful lanes per issued instruction. The model
-ignores divergence INSIDE one distanceToScene evaluation (march lengths), which is why the measured
-wavefront kernel gained nothing from refill: see the text there.
+"lanes" = total thread cost / total lock-step cost = useful lanes per issued instruction. That model
+ignores divergence INSIDE one distanceToScene evaluation; march_model() adds it: the number of table
+lookups per evaluation is heavy-tailed (mean 3.6, tail beyond 15), neighbouring pixel-samples have
+correlated march lengths (9 of 32 lanes busy in the fused kernel's march loop -- what ncu measures),
+unrelated rays do not (5 of 32 -- what the refilling wavefront kernel measured).
 """
 from __future__ import annotations
 
@@ -54,14 +56,65 @@ def site_costs(width: int, height: int, passes: int, vres: int, mat: str) -> np.
     return cost
 
 
+def eval_logs(width: int, height: int, passes: int, vres: int, mat: str) -> np.ndarray:
+    """log[pass, pixel, 256]: the full distanceToScene evaluations of each pixel-sample in order,
+    (call site << 8 | table lookups of its march), 0xffff = end."""
+    sim = HostSim()
+    vol, opts, mcs = build_scene(vres=vres, width=width, height=height, iters=passes, mat=mat)
+    n = width * height
+    log = np.zeros((passes, n, 256), np.uint16)
+    sim.lib.sim_set_eval_buffer.argtypes = [C.c_void_p]
+    vox = np.ascontiguousarray(vol).reshape(-1)
+    px = np.zeros((height, width, 4), np.float32)
+    for p in range(passes):
+        sim.lib.sim_set_eval_buffer(log[p].ctypes.data)
+        sim.lib.sim_render_pixels(vox, np.ascontiguousarray(mcs[p]).reshape(-1), opts[p], px.reshape(-1), n,
+                                  None, 0, None, 0, 2)
+    sim.lib.sim_set_eval_buffer(None)
+    return log
+
+
+def march_model(width: int, height: int, passes: int, vres: int, mat: str, sample: int = 3000) -> None:
+    """Divergence INSIDE the full evaluations: how many lanes are busy in the march loop when the
+    evaluations a warp runs together are (a) the fused kernel's -- the k-th evaluation of the same
+    call site of neighbouring pixel-samples -- or (b) unrelated, as after per-lane refill."""
+    log = eval_logs(width, height, passes, vres, mat)
+    warps = as_warps(log, width, height)
+    valid = warps != 0xFFFF
+    site, cnt = (warps >> 8).astype(np.int32), (warps & 255).astype(np.int32)
+    n_ps = log.shape[0] * log.shape[1]
+    print(f"\nfull evaluations per pixel-sample {valid.sum() / n_ps:.1f}, lookups per evaluation {cnt[valid].sum() / valid.sum():.2f}")
+    rng = np.random.default_rng(0)
+    ev_slots = lk_slots = ev = lk = 0
+    for wi in rng.choice(len(warps), size=min(sample, len(warps)), replace=False):
+        s_, c_, v_ = site[wi], cnt[wi], valid[wi]
+        for st in np.unique(s_[v_]):
+            seqs = [c_[lane][(s_[lane] == st) & v_[lane]] for lane in range(32)]
+            m = max(len(q) for q in seqs)
+            a = np.zeros((32, m), np.int32)
+            for lane, q in enumerate(seqs):
+                a[lane, :len(q)] = q
+                ev += len(q)
+            ev_slots += m
+            lk_slots += int(a.max(axis=0).sum())
+            lk += int(a.sum())
+    print(f"fused kernel (lock step per call site and iteration): {ev / ev_slots:4.1f} of 32 lanes in an evaluation, "
+          f"{lk / lk_slots:4.1f} of 32 in its march loop")
+    allc = cnt[valid]
+    for k in (32, 16):
+        d = rng.choice(allc, size=(200000, k))
+        print(f"{k} unrelated evaluations together (per-lane refill):  {k * d.mean() / d.max(axis=1).mean():4.1f} of {k} lanes in the march loop")
+
+
 def as_warps(cost: np.ndarray, width: int, height: int) -> np.ndarray:
     """[warps, 32 lanes, 64 sites] in the fused kernel's item order (rm_kernels.h:rm_slot_to_pixel)."""
-    passes, n, _ = cost.shape
+    passes, n = cost.shape[0], cost.shape[1]
     ys, xs = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
     slot = (((ys // 4) * (width // 8) + xs // 8) * 32 + (ys % 4) * 8 + xs % 8).reshape(-1)
     order = np.argsort(slot)
-    items = cost[:, order, :].transpose(1, 0, 2).reshape(n * passes, 64)
-    return items.reshape(-1, 32, 64)
+    k = cost.shape[2]
+    items = cost[:, order, :].transpose(1, 0, 2).reshape(n * passes, k)
+    return items.reshape(-1, 32, k)
 
 
 def ao_sites(level):
@@ -166,6 +219,8 @@ def main():
                     loads[(j * tx + i) % world] += pix[j * tile:(j + 1) * tile, i * tile:(i + 1) * tile].sum()
             out[world] = round(float(loads.max() / loads.mean()), 4)
         print(f"  tile {tile:2d}: {out}")
+
+    march_model(args.width // 2, args.height // 2, args.passes, args.vres, args.mat)
 
 
 if __name__ == "__main__":
