@@ -198,10 +198,10 @@ static cudaError_t wave_reserve(RmWaveScratch* w, unsigned cap, int levels, unsi
   if (w->cap < cap || w->levels < levels) {
     cudaFree(w->d_rec); cudaFree(w->d_refl); cudaFree(w->d_pxy);
     w->d_rec = nullptr; w->d_refl = nullptr; w->d_pxy = nullptr; w->cap = 0; w->levels = 0;
-    if ((e = cudaMalloc(&w->d_rec, sizeof(wave::WaveRec) * (size_t)wave::kMaxLevels * cap)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w->d_rec, sizeof(wave::WaveRec) * (size_t)levels * cap)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&w->d_refl, sizeof(float4) * (size_t)cap)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&w->d_pxy, sizeof(float2) * (size_t)cap)) != cudaSuccess) return e;
-    w->cap = cap; w->levels = wave::kMaxLevels;
+    w->cap = cap; w->levels = levels;
   }
   if (w->job_cap < job_cap) {
     cudaFree(w->d_jobs);
@@ -227,7 +227,8 @@ cudaError_t rm_launch_render_wave(const RmOpts& opts, const RmShard& shard, cons
   const unsigned cap = (unsigned)(total < (long long)chunk_items ? total : (long long)chunk_items);
   const int lmax = opts.reflectIter < 0 ? 0 : opts.reflectIter;
   const unsigned job_cap = cap * (unsigned)(opts.numLights + 1) + 1;
-  cudaError_t e = wave_reserve(w, cap, lmax + 1, job_cap);
+  const int levels = lmax + 2 < wave::kMaxLevels ? lmax + 2 : wave::kMaxLevels;  // prepare(lmax) clears the flags of level lmax + 1
+  cudaError_t e = wave_reserve(w, cap, levels, job_cap);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbolAsync(plain::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbolAsync(plain::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
@@ -248,6 +249,7 @@ cudaError_t rm_launch_render_wave(const RmOpts& opts, const RmShard& shard, cons
   unsigned* head = w->d_ctr + 1;
   B.cap = w->cap;
   B.job_cap = w->job_cap;
+  B.levels = levels;
   const unsigned trace_blocks = (unsigned)(num_sms > 0 ? num_sms : 148) * 5u;  // 40 warps per SM
 
   for (long long item0 = 0; item0 < total; item0 += cap) {

@@ -56,6 +56,7 @@ struct WaveBuf {
   WaveJob* jobs;       // [job_cap]
   unsigned* njobs;     // number of jobs appended since the last reset
   unsigned cap, job_cap;
+  int levels;          // record levels allocated (<= kMaxLevels): reflectIter + 2
 };
 
 #if defined(__CUDA_ARCH__)
@@ -196,7 +197,7 @@ template <bool kCount, class Vol>
 RM_DEV void wave_prepare(const WaveBuf& B, unsigned it, Scene& s, const Vol& V, int level) {
   const RmOpts& o = g_opts;
   WaveRec& r = rec_at(B, level, it);
-  if (level + 1 < kMaxLevels) rec_at(B, level + 1, it).flags = 0;
+  if (level + 1 < B.levels) rec_at(B, level + 1, it).flags = 0;
   resolve_record(r, V);
   if (!is_surface(r, level)) return;
   const PixelState st = pixel_state_of(B, it);
@@ -212,7 +213,7 @@ RM_DEV void wave_prepare(const WaveBuf& B, unsigned it, Scene& s, const Vol& V, 
   // the next bounce (sceneColor :421-432): from the primary surface when it reflects at all, from a
   // bounce surface while the budget lasts and the surface is not (nearly) matt
   const bool more = level == 0 ? (m.r0 > 0.0f && o.reflectIter > 0) : (level < o.reflectIter && !(m.r0 < 0.001f));
-  if (more && level + 1 < kMaxLevels) {
+  if (more && level + 1 < B.levels) {
     const float3 bd = reflect3(r.dir, r.nrm);
     const float3 bo = r.pos + bd * 0.0075f;
     WaveRec& nx = rec_at(B, level + 1, it);

@@ -233,7 +233,7 @@ void sim_render_pixels_wave(const uint8_t* vox, const float* mc, const void* opt
   std::vector<float2> pxy(count);
   std::vector<wave::WaveJob> jobs((size_t)(o.numLights + 1) * count + 1);
   unsigned njobs = 0;
-  wave::WaveBuf B{rec.data(), refl.data(), pxy.data(), jobs.data(), &njobs, (unsigned)count, (unsigned)jobs.size()};
+  wave::WaveBuf B{rec.data(), refl.data(), pxy.data(), jobs.data(), &njobs, (unsigned)count, (unsigned)jobs.size(), lmax + 2 < wave::kMaxLevels ? lmax + 2 : wave::kMaxLevels};
   const float4* table = reinterpret_cast<const float4*>(mc);
   unsigned long long cs = 0, ct = 0, co = 0;
   const plain::BrickVolume V{};
