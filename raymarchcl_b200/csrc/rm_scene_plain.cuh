@@ -12,8 +12,14 @@
 // distanceToScene call (the reference recomputes it at every outer iteration and overwrites it,
 // renderer.cl:224-228, so only the last one is ever visible), and both skip the slab test's six
 // IEEE divisions when the ray origin is strictly inside the voxel box (the test then returns
-// exactly +0 whatever the quotients are). Results are identical to the reference's order of
-// operations; the oracle checks that bit for bit on the work counters.
+// exactly +0 whatever the quotients are). The production instantiations (kCount == false) also
+// leave out work that provably cannot change the result -- shadow rays of lights that contribute
+// exactly zero, march samples beyond the distance at which a hit still matters, distanceToScene
+// calls outside the ray's march window (march_window), the ground-only tail of rays that can only
+// miss, AO probes far from the box -- while the counting instantiations (kCount == true) do the
+// reference's full work and report its reference-equivalent counters. Results are identical to the
+// reference's order of operations: tests/hostsim compiles this very header for the host and
+// compares it with the oracle bit for bit; on the GPU the work counters are compared exactly.
 #pragma once
 #include "rm_math.cuh"
 #include "rm_types.h"
