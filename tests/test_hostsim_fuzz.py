@@ -132,3 +132,50 @@ def test_random_options_on_the_gpu(checkers, gpu_renderer, seed, kernel):
     fin = np.isfinite(ref)
     assert np.array_equal(np.isfinite(px), fin)
     assert (np.abs(px - ref)[fin] <= 2e-5 * np.maximum(1.0, np.abs(ref[fin]))).all()
+
+
+def _reference_safe(fields):
+    """Keep the randomised options inside the domain where the reference's own text has defined behaviour: a
+    trace that runs out of iterations returns (int)ground-distance as its material id (renderer.cl:211) and
+    the reference then indexes opts->materials[] out of bounds (:392, :417) -- a wild read, a crash for far
+    misses (maxDist 1e4) or a plane above the eye. The restatement and the kernels clamp the index."""
+    f = dict(fields)
+    f["maxIter"] = 128
+    f["maxDist"] = min(float(f["maxDist"]), 30.0)
+    f["groundY"] = max(float(f["groundY"]), 1.05)
+    f["eyePos"] = [f["eyePos"][0], max(float(f["eyePos"][1]), -0.5), f["eyePos"][2]]
+    return f
+
+
+def _pin_worker(seeds):
+    """Runs in a child process (a wild read of the reference must not take the test session down)."""
+    build_oracle.build(verbose=False)
+    orc, ref = refso.load("oracle"), refso.load("ref_strict")
+    bad = []
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        vres = int(rng.choice([32, 48, 64, 96]))
+        vol = VOLUMES[str(rng.choice(list(VOLUMES)))](vres)
+        fields = _reference_safe(_random_fields(rng, vres))
+        opts = [encode_render_opts({**fields, "frameBlend": 0.5, "time": fields["time"] + 0.333 * i}) for i in range(2)]
+        mcs = [generate_scatter_offsets(0x4000, 77 + seed + i) for i in range(2)]
+        pr, cr = ref.render_frame(vol, mcs, opts, W, H)
+        po, co = orc.render_frame(vol, mcs, opts, W, H)
+        same = (pr.view(np.uint32) == po.view(np.uint32)) | (np.isnan(pr) & np.isnan(po))
+        if not same.all() or not np.array_equal(cr, co):
+            bad.append((seed, int((~same).any(axis=-1).sum()), cr.tolist(), co.tolist()))
+    return bad
+
+
+def test_random_options_oracle_is_bit_identical_to_the_reference_text(ref_strict):
+    """The pin of the C restatement itself on randomised blobs: oracle/rm_oracle.c against the reference's own
+    kernel text (oracle/_ref/libref_strict.so, built from /root/reference/resources/renderer.cl), bit for bit on
+    accumulators and work counters, 80 seeds. Skipped where oracle/_ref has not been built."""
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(1) as pool:
+        res = pool.apply_async(_pin_worker, (list(range(0, 160, 2)),))
+        try:
+            bad = res.get(timeout=180)
+        except Exception as e:  # the child died: the reference read out of bounds
+            pytest.fail(f"the reference text crashed or timed out on a randomised blob: {e!r}")
+    assert not bad, bad
