@@ -172,7 +172,7 @@ def test_random_options_oracle_is_bit_identical_to_the_reference_text(ref_strict
     kernel text (oracle/_ref/libref_strict.so, built from /root/reference/resources/renderer.cl), bit for bit on
     accumulators and work counters, 80 seeds. Skipped where oracle/_ref has not been built."""
     import multiprocessing as mp
-    with mp.get_context("fork").Pool(1) as pool:
+    with mp.get_context("spawn").Pool(1) as pool:  # (not fork: the parent already runs OpenMP threads)
         res = pool.apply_async(_pin_worker, (list(range(0, 160, 2)),))
         try:
             bad = res.get(timeout=180)
