@@ -4,7 +4,7 @@
 
 A "step" is one frame of the hot path: all RenderImage passes + TonemapImage (+ the one
 framebuffer gather when N > 1). One process per GPU (torchrun for N > 1); the frame is sharded by
-interleaved 32x32 tiles with no data-path collective until the final gather ("weak" is wrong for
+interleaved tiles with no data-path collective until the final gather ("weak" is wrong for
 a fixed frame: total work is fixed, so `scaling` = "strong").
 
   value     device-resident throughput: volume, tables and opts already in HBM; per-step CUDA
@@ -69,11 +69,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="fast", choices=["fast", "plain", "warp", "wave"])
+    ap.add_argument("--kernel", default="fast", choices=["fast", "plain", "warp", "wave", "bricks"])
     ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE",
                     help="rm_set_option tuning knob of the fast kernel (results do not depend on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed frame")
     return ap.parse_args()
 
 
@@ -87,14 +88,66 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload: str, kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, taken from
-    the committed ncu capture summary (profiles/traffic.json), or None."""
+def ncu_capture(workload: str, kernel: str) -> dict:
+    """What the committed ncu capture of the dominant kernel says (profiles/traffic.json, written from the
+    `ncu --set full` summary under profiles/): DRAM bytes, L2 bytes, issue-active %, lanes per
+    instruction -- per launch. Empty when there is no capture of this workload/kernel pair."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p))[f"{workload}:{kernel}"]["dram_bytes_per_launch"]
+        return json.load(open(p))[f"{workload}:{kernel}"]
     except Exception:
-        return None
+        return {}
+
+
+PARITY_TOL = 2e-5  # per channel, relative to max(1, |ref|): the bar of tests/test_gpu_parity.py
+
+
+def parity_check(oracle_lib, vol, mcs, opts, w, h, accum, argb, stride):
+    """Compare every `stride`-th pixel of the TIMED frame (fp32 accumulator where this rank rendered it,
+    ARGB words of the assembled frame) with the strict oracle on the same inputs. Raises when the
+    2e-5 / 1 LSB bar is broken: a fast frame that differs from the reference's is not a result."""
+    ids = np.arange(0, w * h, stride, dtype=np.int32)
+    ref_px, _ = oracle_lib.render_frame(vol, mcs, opts, w, h, ids=ids)
+    ref_argb = oracle_lib.tonemap(ref_px, opts[0]).reshape(-1)[ids]
+    ref = ref_px.reshape(-1, 4)[ids].astype(np.float64)
+    out = {"pixels": int(ids.size), "sample": f"every {stride}th pixel id, all {len(opts)} passes", "tolerance": PARITY_TOL}
+    got_argb = argb.reshape(-1)[ids].astype(np.int64)
+    lsb = 0
+    for sh in (16, 8, 0):
+        lsb = max(lsb, int(np.abs(((got_argb >> sh) & 255) - ((ref_argb.astype(np.int64) >> sh) & 255)).max()))
+    out["argb_max_lsb"] = lsb
+    out["argb_identical_frac"] = float((got_argb == ref_argb.astype(np.int64)).mean())
+    if accum is not None:
+        got = accum.reshape(-1, 4)[ids].astype(np.float64)
+        mine = got[:, 3] == 1.0  # pixels this rank rendered (alpha is written as 1)
+        rel = np.abs(got[mine, :3] - ref[mine, :3]) / np.maximum(1.0, np.abs(ref[mine, :3]))
+        out["accum_pixels"] = int(mine.sum())
+        out["max_rel_err"] = float(rel.max()) if rel.size else 0.0
+        out["nan"] = bool(np.isnan(got[mine]).any())
+    ok = lsb <= 1 and out["argb_identical_frac"] >= 0.995 and out.get("max_rel_err", 0.0) <= PARITY_TOL and not out.get("nan", False)
+    out["ok"] = bool(ok)
+    return out
+
+
+def counters_check(r, oracle_lib, vol, mcs, opts, w, h, iters, rank, world, resident_render):
+    """The metric's numerator is the kernel's own step counter: pin it. The counting kernel renders the tiles
+    of one shard of 64 and must report exactly the oracle's inner-step / tap / sphere-trace counts there."""
+    from raymarchcl_b200.dist import ShardLayout
+    sub = 64
+    idx = ShardLayout(w, h, sub, *TILE).slot_pixel_index(0)
+    ids = np.sort(idx[idx >= 0]).astype(np.int32)
+    r.set_tile_shard(0, sub, *TILE)
+    r.clear_accum(w, h)
+    r.reset_stats()
+    r.count_work(True)
+    r.render_resident(0, iters)
+    st = r.stats()
+    r.count_work(False)
+    r.set_tile_shard(rank, world, *TILE)
+    r.clear_accum(w, h)
+    _, ref_cnt = oracle_lib.render_frame(vol, mcs, opts, w, h, ids=ids)
+    got = [int(st["steps"]), int(st["taps"]), int(st["outer_iters"])]
+    return got == [int(x) for x in ref_cnt], int(ids.size)
 
 
 class ClockSampler:
@@ -247,7 +300,7 @@ def run_b200(args):
 
     layout = ShardLayout(w, h, world, *TILE)
     r = Renderer(local)
-    r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2, "wave": 3}[args.kernel])
+    r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2, "wave": 3, "bricks": 4}[args.kernel])
     for kv in args.opt:
         k, v = kv.split("=")
         r.set_option(int(k), int(v))
@@ -258,6 +311,12 @@ def run_b200(args):
     frame1 = torch.empty(w * h, dtype=torch.int32, device=dev) if world == 1 else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     argb_host = torch.empty(w * h, dtype=torch.int32).pin_memory()
+    # the default kernel writes the ARGB words while it renders: straight into the buffer the frame is
+    # assembled from (the gather's send buffer when sharded), so that TonemapImage costs no extra pass
+    if world == 1:
+        r.set_argb_target(frame1.data_ptr(), packed=False)
+    else:
+        r.set_argb_target(gather.local.data_ptr(), packed=True)
 
     def barrier():
         if world > 1:
@@ -310,14 +369,260 @@ def run_b200(args):
         st = r.stats()
         t = torch.tensor([dev_ms, st["render_ms"]], dtype=torch.float64, device=dev)
         launches = torch.tensor([st["kernel_launches"]], dtype=torch.int64, device=dev)
+        per_rank = [t.clone() for _ in range(world)]
         if world > 1:
+            dist.all_gather(per_rank, t)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(launches)
         dev_ms, render_ms = t.tolist()
+        rank_render_ms = [float(x[1]) / args.steps for x in per_rank]
+        rank_step_ms = [float(x[0]) / args.steps for x in per_rank]
+
+        # ---- parity of the frame that was just timed (production kernel, last timed step) ----
+        parity = None
+        if not args.no_parity:
+            accum_last = r.read_accum()
+            if world == 1:
+                argb_last = frame1.cpu().numpy().view(np.uint32)
+            else:
+                fr = resident_frame()
+                argb_last = fr.cpu().numpy().view(np.uint32) if rank == 0 else None
+            from oracle import build_oracle, refso
+            build_oracle.build(verbose=False)
+            orc = refso.load("oracle")
+            stride = 64 if w * h * iters > 4_000_000 else 1
+            if rank == 0:
+                parity = parity_check(orc, vol, mcs, opts, w, h, accum_last, argb_last, stride)
+            ok, npx = counters_check(r, orc, vol, mcs, opts, w, h, iters, rank, world, resident_frame) if rank == 0 else (True, 0)
+            if rank == 0:
+                parity["counters_exact"] = bool(ok)
+                parity["counters_pixels"] = npx
+                parity["checker"] = "oracle/rm_oracle.c (strict fp32 restatement, pinned to the reference text)"
+            barrier()
 
         # ---- end to end through the host-buffer calls ----
         e2e = None
         if not args.no_e2e:
+            if world == 1:
+                r.set_argb_target(None)  # rm_tonemap reads the context's own frame, which the render launch then fills
+
+            def host_frame():
+                r.set_volume(vol_host)
+                r.clear_accum(w, h)
+                r.render_frame(opts, mcs_host)
+                if world == 1:
+                    return r.tonemap(opts[0], out=argb_host.numpy().view(np.uint32))
+                r.tonemap_device(opts[0], gather.local.data_ptr(), packed=True)
+                fr = gather.gather()
+                if rank == 0:
+                    argb_host.copy_(fr, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                return None
+
+            for _ in range(max(1, min(args.warmup, 3))):
+                host_frame()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                host_frame()
+            barrier()
+            e2e_s = time.perf_counter() - t0
+            te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e_s = te.item()
+            h2d = vol.size + iters * (65536 * 4 + 544)
+            e2e = {"value": steps_frame * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s",
+                   "frames_per_s": args.steps / e2e_s, "ms_per_step": 1e3 * e2e_s / args.steps,
+                   "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(w * h * 4),
+                   "path": "rm_set_volume + rm_clear_accum + rm_render_frame + rm_tonemap, pinned host buffers"
+                           + ("" if world == 1 else "; every rank uploads its own copy of the inputs")}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = dev_ms / args.steps
+    value = steps_frame / (ms_per_step * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    # per launch of the render kernel: frame bytes / launches-per-frame over avg launch duration
+    kernel_s_per_frame = render_ms * 1e-3 / args.steps
+    achieved = (steps_frame / world + taps_frame / world) / kernel_s_per_frame / 1e9  # per GPU
+    cap = ncu_capture(args.workload, args.kernel)
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": cap.get("dram_bytes_per_launch"),
+            # the secondary, honest ceilings: what the same ncu capture says about L2 and issue slots
+            "l2_bytes": cap.get("l2_bytes_per_launch"),
+            "issue_active_pct": cap.get("issue_active_pct"),
+            "lanes_per_instr": cap.get("lanes_per_instr"),
+            "warps_active_pct": cap.get("warps_active_pct"),
+            "ncu_capture": cap.get("source"),
+            "peak_source": peak_src,
+            "kernel": {"fast": "k_render_persist (persistent warps, distance map in shared memory via bulk TMA, all passes of a "
+                               "frame + blend + tonemap in one launch)",
+                       "bricks": "k_render_bricks (round-1 default: one thread per item, + k_blend_passes)",
+                       "warp": "k_render_warp (persistent, all passes of a frame in one launch)",
+                       "wave": "k_wave_* pipeline (primary, prepare / persistent trace per level, final)",
+                       "plain": "k_render_plain (one launch per pass)"}[args.kernel],
+            "algorithmic_bytes_per_frame": steps_frame + taps_frame,
+            "kernel_ms_per_frame": kernel_s_per_frame * 1e3,
+            "kernel_share_of_step": kernel_s_per_frame * 1e3 / ms_per_step,
+            "note": "1 B per reference-equivalent voxel fetch (inner steps + occupancy taps). The volume and its "
+                    "derived tables are L1/L2/shared-memory resident and most fetches are elided, so DRAM traffic stays "
+                    "far below the algorithmic bytes by design; the kernel is instruction-issue bound (DESIGN.md 4-5)"}
+
+    line = {
+        "impl": "reference", "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frames_per_s": value * 1e6 / (steps_sample * stride) if steps_sample else None,
+        "frames_per_s_note": "extrapolated from the sample by the step ratio",
+        "config": {"workload": wl["name"], "reference_build": name, "host": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    _emit(line)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from raymarchcl_b200 import _lib
+    from raymarchcl_b200.dist import FrameGatherer, ShardLayout
+    from raymarchcl_b200.renderer import Renderer
+    from tests.scenes import build_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the render op has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = WORKLOADS[args.workload]
+    sc = wl["scene"]
+    w, h, iters = sc["width"], sc["height"], sc["iters"]
+    vol, opts, mcs = build_scene(**sc)
+    # host-side inputs of the end-to-end arm live in pinned memory
+    vol_pinned = torch.from_numpy(np.ascontiguousarray(vol)).pin_memory()
+    vol_host = vol_pinned.numpy()
+    mcs_pinned = [torch.from_numpy(np.ascontiguousarray(m)).pin_memory() for m in mcs]
+    mcs_host = [m.numpy() for m in mcs_pinned]
+
+    layout = ShardLayout(w, h, world, *TILE)
+    r = Renderer(local)
+    r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2, "wave": 3, "bricks": 4}[args.kernel])
+    for kv in args.opt:
+        k, v = kv.split("=")
+        r.set_option(int(k), int(v))
+    r.set_tile_shard(rank, world, *TILE)
+    stream = torch.cuda.Stream(device=dev)
+    r.set_stream(stream.cuda_stream)
+    gather = FrameGatherer(layout, rank, dev, torch.int32, renderer=r) if world > 1 else None
+    frame1 = torch.empty(w * h, dtype=torch.int32, device=dev) if world == 1 else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    argb_host = torch.empty(w * h, dtype=torch.int32).pin_memory()
+    # the default kernel writes the ARGB words while it renders: straight into the buffer the frame is
+    # assembled from (the gather's send buffer when sharded), so that TonemapImage costs no extra pass
+    if world == 1:
+        r.set_argb_target(frame1.data_ptr(), packed=False)
+    else:
+        r.set_argb_target(gather.local.data_ptr(), packed=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def resident_frame():
+        """all passes + tonemap (+ gather) from inputs resident in HBM; returns the frame on rank 0"""
+        r.clear_accum(w, h)
+        r.render_resident(0, iters)
+        if world == 1:
+            r.tonemap_device(opts[0], frame1.data_ptr(), packed=False)
+            return frame1
+        r.tonemap_device(opts[0], gather.local.data_ptr(), packed=True)
+        return gather.gather()
+
+    # ---- inputs into HBM, work count (untimed) ----
+    with torch.cuda.stream(stream):
+        r.set_volume(vol_host)
+        r.clear_accum(w, h)
+        r.upload_passes(opts, mcs)
+        r.reset_stats()
+        r.count_work(True)
+        resident_frame()
+        st = r.stats()
+        r.count_work(False)
+        work = torch.tensor([st["steps"], st["taps"], st["outer_iters"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(work)
+        steps_frame, taps_frame, outer_frame = [int(x) for x in work.tolist()]
+
+        # ---- device-resident timed loop ----
+        sampler = ClockSampler(local) if rank == 0 else None  # polling starts during the warm-up
+        for _ in range(args.warmup):
+            resident_frame()
+            flush.zero_()
+        barrier()
+        r.reset_stats()
+        t_wall0 = time.perf_counter()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ev:
+            a.record(stream)
+            resident_frame()
+            b.record(stream)
+            flush.zero_()  # L2 flush between timed iterations, outside the event pair
+        barrier()
+        t_wall1 = time.perf_counter()
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        st = r.stats()
+        t = torch.tensor([dev_ms, st["render_ms"]], dtype=torch.float64, device=dev)
+        launches = torch.tensor([st["kernel_launches"]], dtype=torch.int64, device=dev)
+        per_rank = [t.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, t)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches)
+        dev_ms, render_ms = t.tolist()
+        rank_render_ms = [float(x[1]) / args.steps for x in per_rank]
+        rank_step_ms = [float(x[0]) / args.steps for x in per_rank]
+
+        # ---- parity of the frame that was just timed (production kernel, last timed step) ----
+        parity = None
+        if not args.no_parity:
+            accum_last = r.read_accum()
+            if world == 1:
+                argb_last = frame1.cpu().numpy().view(np.uint32)
+            else:
+                fr = resident_frame()
+                argb_last = fr.cpu().numpy().view(np.uint32) if rank == 0 else None
+            from oracle import build_oracle, refso
+            build_oracle.build(verbose=False)
+            orc = refso.load("oracle")
+            stride = 64 if w * h * iters > 4_000_000 else 1
+            if rank == 0:
+                parity = parity_check(orc, vol, mcs, opts, w, h, accum_last, argb_last, stride)
+            ok, npx = counters_check(r, orc, vol, mcs, opts, w, h, iters, rank, world, resident_frame) if rank == 0 else (True, 0)
+            if rank == 0:
+                parity["counters_exact"] = bool(ok)
+                parity["counters_pixels"] = npx
+                parity["checker"] = "oracle/rm_oracle.c (strict fp32 restatement, pinned to the reference text)"
+            barrier()
+
+        # ---- end to end through the host-buffer calls ----
+        e2e = None
+        if not args.no_e2e:
+            if world == 1:
+                r.set_argb_target(None)  # rm_tonemap reads the context's own frame, which the render launch then fills
+
             def host_frame():
                 r.set_volume(vol_host)
                 r.clear_accum(w, h)
@@ -386,6 +691,9 @@ def run_b200(args):
                    "steps_per_frame": steps_frame, "taps_per_frame": taps_frame,
                    "outer_iters_per_frame": outer_frame, "pixel_samples_per_frame": w * h * iters},
         "roofline": roof,
+        "parity": parity,
+        "per_rank": {"render_ms": {"min": min(rank_render_ms), "mean": sum(rank_render_ms) / world, "max": max(rank_render_ms)},
+                     "step_ms": {"min": min(rank_step_ms), "mean": sum(rank_step_ms) / world, "max": max(rank_step_ms)}},
         "e2e": e2e,
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
@@ -410,6 +718,8 @@ def run_b200(args):
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not (parity["ok"] and parity["counters_exact"]):
+        raise SystemExit(f"bench.py: the timed frame does NOT match the oracle: {parity}")
 
 
 def main():

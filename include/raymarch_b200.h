@@ -34,7 +34,7 @@ extern "C" {
 
 #define RM_OPTS_BYTES   544    /* sizeof(TRenderOpts), renderer.cl:35-78 */
 #define RM_TABLE_FLOATS 65536  /* 0x4000 float4, renderer.cl:143 / core.clj:138 */
-#define RM_ABI_VERSION  1
+#define RM_ABI_VERSION  2
 
 typedef struct rm_ctx rm_ctx;
 
@@ -70,19 +70,22 @@ typedef struct rm_stats {
 
 typedef enum rm_option {
   RM_OPT_COUNT_WORK = 1,   /* 0 (default) | 1: gather reference-equivalent work counters */
-  RM_OPT_KERNEL = 2,       /* which RenderImage kernel: 0 = one thread per (pixel, pass) over the bit-brick
-                              volume; 1 = plain, over the raw byte volume (comparison kernel);
+  RM_OPT_KERNEL = 2,       /* which RenderImage kernel: 0 = default: persistent warps over the bit-brick volume,
+                              distance map staged into shared memory by bulk TMA, blend + tonemap folded in;
+                              1 = plain, over the raw byte volume (comparison kernel);
                               2 = warp-scheduled persistent state machine over the bit-brick volume;
-                              3 = wavefront pipeline (stages + a persistent, refilling trace kernel).
-                              All four produce identical results. */
+                              3 = wavefront pipeline (stages + a persistent, refilling trace kernel);
+                              4 = one thread per (pixel, pass) over the bit-brick volume + blend kernel
+                              (round 1's default). All five produce identical results. */
   /* tuning knobs of the fast kernel; none of them changes results */
   RM_OPT_CELL_SHIFT = 3,   /* macro-cell edge of the distance map = 1<<value voxels; 0 = auto (~res/64) */
   RM_OPT_FUSE_LIMIT = 6,   /* max passes rendered by one launch (1..32) */
   RM_OPT_TRIP_LIMIT = 7,   /* watchdog of kernel 2: scheduling trips a warp may take per launch before
                               the launch is abandoned with RM_ERR_CUDA (default 2^28) */
   RM_OPT_WAVE_CHUNK = 8,   /* kernel 3: (pixel, pass) items per chunk of the pipeline (1024..2^24, default 2^24) */
-  RM_OPT_WAVE_REFILL = 9   /* kernel 3: the trace kernel hands new rays to idle lanes once this many lanes of a
+  RM_OPT_WAVE_REFILL = 9,  /* kernel 3: the trace kernel hands new rays to idle lanes once this many lanes of a
                               warp are idle (1 = at once ... 32 = the warp starts 32 rays together) */
+  RM_OPT_PERSIST_BLOCK = 10 /* kernel 0: threads of the one resident block per SM: 0 = default, 512, 768, 1024 */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */
@@ -95,6 +98,9 @@ const char* rm_last_error(const rm_ctx* ctx);
 /* ---- inputs ---- */
 /* v-buf upload (vio/load-volume, io.clj:19-33 + {:write [.. v-buf]}, core.clj:81). */
 int rm_set_volume(rm_ctx* ctx, const uint8_t* voxels, int rx, int ry, int rz);
+/* The same from DEVICE memory (a volume assembled over NVLink or written by another kernel): one
+ * device-to-device copy on the context's stream. */
+int rm_set_volume_device(rm_ctx* ctx, const void* d_voxels, int rx, int ry, int rz);
 /* The same from a .vox file as vio/save-volume writes it (io.clj:9-17: "VOXEL", 3 x int32 big-endian,
  * element-size byte, raw bytes): reads through pinned memory and uploads. The extents are returned
  * through the optional out pointers (the caller needs them for TRenderOpts.voxelRes). */
@@ -113,17 +119,36 @@ int rm_render_frame(rm_ctx* ctx, const void* const* opts, const float* const* mc
 int rm_tonemap(rm_ctx* ctx, const void* opts, size_t opts_len, uint32_t* argb_out);
 /* Parity hook: copy the fp32 RGBA accumulator to the host (the reference never reads p-buf). */
 int rm_read_accum(rm_ctx* ctx, float* rgba_out);
+/* "TonemapImage" + an ASYNCHRONOUS :read [:out] for animation loops (test-anim, core.clj:199-212): returns
+ * once the work is queued; the ARGB words land in argb_out (ideally pinned host memory) some time before
+ * rm_wait(ctx, slot) returns. Two frames are kept on the device, so the render calls that follow write
+ * the next frame while this one is still travelling. slot is 0 or 1. */
+int rm_tonemap_async(rm_ctx* ctx, const void* opts, size_t opts_len, uint32_t* argb_out, int slot);
+int rm_wait(rm_ctx* ctx, int slot);
+/* Page-locked host memory for rm_tonemap_async / rm_render_frame inputs (a JVM host wraps it in a direct
+ * ByteBuffer): copies to and from it are truly asynchronous and run at full PCIe rate. */
+int rm_host_alloc(rm_ctx* ctx, size_t bytes, void** out_ptr);
+int rm_host_free(rm_ctx* ctx, void* ptr);
 
 /* ---- resident-input variants (inputs already in HBM when the timed region starts) ---- */
 /* Store the per-pass opts blobs and tables on the device once (test-anim keeps them across frames,
  * core.clj:189-208) ... */
 int rm_upload_passes(rm_ctx* ctx, const void* const* opts, const float* const* mc, int iter);
 /* (mc == NULL: use the tables produced in place by rm_generate_scatter_tables.) */
+/* update-render-option-buffer (core.clj:108-117) for the resident passes: new opts blobs (a new camera),
+ * same tables. iter must equal the uploaded pass count. 544 bytes per pass cross the bus. */
+int rm_update_opts(rm_ctx* ctx, const void* const* opts, int iter);
 /* ... then render passes [first, first+count) from the resident copies; no host traffic. */
 int rm_render_resident(rm_ctx* ctx, int first, int count);
 /* Tonemap into device memory the caller owns (e.g. a torch tensor used for the NCCL gather);
  * `packed` != 0 writes only this context's tile shard, tile-major (see rm_set_tile_shard). */
 int rm_tonemap_device(rm_ctx* ctx, const void* opts, size_t opts_len, void* d_argb, int packed);
+/* Register caller-owned device memory (width*height words, or rm_shard_slots() words when packed) that
+ * the default render kernel fills with the ARGB words of the frame WHILE it renders; a later
+ * rm_tonemap_device(opts, same pointer, same packing) with the launch's gamma then costs nothing. The
+ * memory may belong to a peer GPU with access enabled (every GPU stores its tiles into one frame over
+ * NVLink). NULL restores the context's own frame. */
+int rm_set_argb_target(rm_ctx* ctx, void* d_argb, int packed);
 /* Copy the accumulator into device memory the caller owns (same packing rule). */
 int rm_copy_accum_device(rm_ctx* ctx, void* d_rgba, int packed);
 int rm_sync(rm_ctx* ctx);

@@ -24,6 +24,7 @@ RM_OPT_FUSE_LIMIT = 6
 RM_OPT_TRIP_LIMIT = 7
 RM_OPT_WAVE_CHUNK = 8
 RM_OPT_WAVE_REFILL = 9
+RM_OPT_PERSIST_BLOCK = 10
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
@@ -31,7 +32,7 @@ EXPORTS = [
     "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
     "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
     "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_shard_slots", "rm_unpack_shards", "rm_set_option", "rm_get_stats",
-    "rm_reset_stats",
+    "rm_reset_stats", "rm_set_volume_device", "rm_tonemap_async", "rm_wait", "rm_update_opts", "rm_set_argb_target", "rm_host_alloc", "rm_host_free",
 ]
 
 
@@ -101,5 +102,12 @@ def load() -> C.CDLL:
     lib.rm_set_option.argtypes = [vp, ip, C.c_int64]
     lib.rm_get_stats.argtypes = [vp, C.POINTER(RmStats)]
     lib.rm_reset_stats.argtypes = [vp]
+    lib.rm_set_volume_device.argtypes = [vp, vp, ip, ip, ip]
+    lib.rm_tonemap_async.argtypes = [vp, vp, sz, vp, ip]
+    lib.rm_wait.argtypes = [vp, ip]
+    lib.rm_update_opts.argtypes = [vp, C.POINTER(vp), ip]
+    lib.rm_set_argb_target.argtypes = [vp, vp, ip]
+    lib.rm_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.rm_host_free.argtypes = [vp, vp]
     _lib = lib
     return lib

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libraymarch_b200.so")
-SOURCES = ["rm_api.cu", "rm_kernels.cu", "rm_accel.cu", "rm_render_fast.cu", "rm_render_warp.cu", "rm_render_wave.cu", "rm_generate.cu"]
+SOURCES = ["rm_api.cu", "rm_kernels.cu", "rm_accel.cu", "rm_render_fast.cu", "rm_render_persist.cu", "rm_render_warp.cu", "rm_render_wave.cu", "rm_generate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]

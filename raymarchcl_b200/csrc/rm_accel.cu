@@ -107,6 +107,17 @@ k_cheb_axis(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int mx, i
   out[c] = (uint8_t)best;
 }
 
+// 4 bits per cell: min(dist, 15), two cells per byte (low nibble = even cell)
+__global__ void __launch_bounds__(256)
+k_pack_nibbles(const uint8_t* __restrict__ dist, long long cells, uint8_t* __restrict__ nib, unsigned nib_bytes) {
+  const long long b = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (b >= nib_bytes) return;
+  const long long c = 2 * b;
+  const int lo = c < cells ? min((int)__ldg(dist + c), 15) : 0;
+  const int hi = c + 1 < cells ? min((int)__ldg(dist + c + 1), 15) : 0;
+  nib[b] = (uint8_t)(lo | (hi << 4));
+}
+
 }  // namespace
 
 cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso, int cell_shift,
@@ -129,10 +140,11 @@ cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso
     st->brick_capacity = nb;
   }
   if (st->cell_capacity < nc) {
-    cudaFree(st->d_dist); cudaFree(st->d_tmp);
-    st->d_dist = st->d_tmp = nullptr; st->cell_capacity = 0;
+    cudaFree(st->d_dist); cudaFree(st->d_tmp); cudaFree(st->d_nib);
+    st->d_dist = st->d_tmp = st->d_nib = nullptr; st->cell_capacity = 0;
     if ((e = cudaMalloc(&st->d_dist, nc)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&st->d_tmp, nc)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&st->d_nib, (nc / 2 + 16) & ~(size_t)15)) != cudaSuccess) return e;
     st->cell_capacity = nc;
   }
   if (!st->d_flag && (e = cudaMalloc(&st->d_flag, sizeof(unsigned))) != cudaSuccess) return e;
@@ -144,6 +156,8 @@ cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso
   k_cheb_axis<<<cb, 256, 0, stream>>>(st->d_dist, st->d_tmp, a.mx, a.my, a.mz, 0);
   k_cheb_axis<<<cb, 256, 0, stream>>>(st->d_tmp, st->d_dist, a.mx, a.my, a.mz, 1);
   k_cheb_axis<<<cb, 256, 0, stream>>>(st->d_dist, st->d_tmp, a.mx, a.my, a.mz, 2);
+  const unsigned nib_bytes = (unsigned)(((nc + 1) / 2 + 15) & ~(size_t)15);
+  k_pack_nibbles<<<(nib_bytes + 255) / 256, 256, 0, stream>>>(st->d_tmp, (long long)nc, st->d_nib, nib_bytes);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   unsigned differ = 1;
   if ((e = cudaMemcpyAsync(&differ, st->d_flag, sizeof differ, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
@@ -151,13 +165,15 @@ cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso
   a.solid = st->d_solid;
   a.occ = differ ? st->d_occ : st->d_solid;  // identical predicates unless some voxel == isoVal
   a.dist = st->d_tmp;
+  a.nib = st->d_nib;
+  a.nib_bytes = nib_bytes;
   st->iso = iso;
   st->valid = true;
-  st->launches = 5;
+  st->launches = 6;
   return cudaSuccess;
 }
 
 void rm_accel_free(RmAccelStorage* st) {
-  cudaFree(st->d_solid); cudaFree(st->d_occ); cudaFree(st->d_dist); cudaFree(st->d_tmp); cudaFree(st->d_flag);
+  cudaFree(st->d_solid); cudaFree(st->d_occ); cudaFree(st->d_dist); cudaFree(st->d_tmp); cudaFree(st->d_nib); cudaFree(st->d_flag);
   *st = RmAccelStorage{};
 }

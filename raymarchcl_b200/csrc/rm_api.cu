@@ -36,9 +36,23 @@ struct rm_ctx {
 
   // framebuffer ("p-buf", "q-buf")
   float4* d_accum = nullptr;
-  uint32_t* d_argb = nullptr;
+  uint32_t* d_argb2[2] = {nullptr, nullptr};  // two ARGB frames: one is read back while the next is rendered
+  int argb_cur = 0;                           // the one the current frame is written to
   int W = 0, H = 0;
   size_t fb_capacity = 0;  // pixels allocated
+  // TonemapImage folded into the render launch (rm_render_persist.cu): where the default kernel
+  // writes the ARGB words of the frame so far, and whether that buffer matches the accumulator
+  uint32_t* argb_target = nullptr;   // caller-owned device buffer (rm_set_argb_target) or null = d_argb2[argb_cur]
+  int argb_target_packed = 0;
+  const void* argb_fresh_ptr = nullptr;  // buffer that holds tonemap(accum, argb_fresh_gamma) right now, or null
+  int argb_fresh_packed = 0;
+  float argb_fresh_gamma = 0.f;
+  // asynchronous read-back (rm_tonemap_async / rm_wait)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t frame_ready[2] = {nullptr, nullptr};  // main stream: ARGB buffer b complete
+  cudaEvent_t copy_done[2] = {nullptr, nullptr};    // copy stream: read-back of buffer b complete
+  bool copy_pending[2] = {false, false};
+  int slot_buffer[2] = {-1, -1};                    // which ARGB buffer the read-back of slot s uses
 
   // per-pass inputs
   float4* d_tables = nullptr;  // resident scatter tables, 16384 float4 each
@@ -60,7 +74,9 @@ struct rm_ctx {
   size_t colour_capacity = 0;       // float4 elements
   int num_sms = 0;
   cudaEvent_t launch_done = nullptr;  // completion of this context's last render launch (DeviceGuard)
-  unsigned long long* d_queue = nullptr;  // work queue head of the warp kernel
+  unsigned long long* d_queue = nullptr;  // [0] work queue head of the warp kernel, [1] bundle tickets of the default kernel
+  unsigned long long queue_base = 0;      // expected value of d_queue[1] (monotonic, rm_launch_render_persist)
+  int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
   int warp_blocks[2] = {0, 0};            // resident blocks per SM of the warp kernel [plain, counting]
@@ -157,6 +173,8 @@ int ensure_tables(rm_ctx* c, int n) {
   if (c->table_capacity >= n) return RM_OK;
   if (c->d_tables) cudaFree(c->d_tables);
   c->d_tables = nullptr; c->table_capacity = 0;
+  c->generated_tables = 0;  // whatever was generated in place lived in the old allocation
+  c->resident = 0;
   RM_CUDA(c, cudaMalloc(&c->d_tables, (size_t)n * RM_TABLE_FLOATS * sizeof(float)));
   c->table_capacity = n;
   return RM_OK;
@@ -249,29 +267,60 @@ bool fusable(const RmOpts& a, const RmOpts& b) {
   return std::memcmp(&x, &y, sizeof(RmOpts)) == 0;
 }
 
+// Scope of one timed, guarded launch: takes DeviceGuard.mu and an event pair on construction and
+// releases both on EVERY way out of the scope.
+struct LaunchScope {
+  rm_ctx* c;
+  EventPair t;
+  explicit LaunchScope(rm_ctx* ctx) : c(ctx), t(begin_timed(ctx, 0)) { guard_before_launch(c); }
+  ~LaunchScope() {
+    guard_after_launch(c);
+    end_timed(c, t);
+  }
+  LaunchScope(const LaunchScope&) = delete;
+  LaunchScope& operator=(const LaunchScope&) = delete;
+};
+
+// the ARGB buffer the default kernel writes while it renders (null: none)
+uint32_t* fused_argb_target(rm_ctx* c, int* packed) {
+  if (c->argb_target) { *packed = c->argb_target_packed; return c->argb_target; }
+  *packed = 0;
+  // the context's own frame is pixel-indexed: only complete when this context owns every pixel
+  return c->shard.world == 1 ? c->d_argb2[c->argb_cur] : nullptr;
+}
+
 // RenderImage for passes [0, n) whose tables are contiguous at d_tables, in submission order.
 int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables) {
   const size_t tstride = RM_TABLE_FLOATS / 4;
   RmCounters* cnt = c->count_work ? c->d_counters : nullptr;
+  c->argb_fresh_ptr = nullptr;  // the accumulator is about to change
   if (c->kernel_kind == 1) {
     for (int i = 0; i < n; ++i) {
-      EventPair t = begin_timed(c, 0);
-      guard_before_launch(c);
-      cudaError_t e = rm_launch_render_plain(c->d_vox, d_tables + i * tstride, passes[i], c->shard, c->d_accum, cnt, c->stream);
-      guard_after_launch(c);
-      end_timed(c, t);
+      cudaError_t e;
+      {
+        LaunchScope scope(c);
+        e = rm_launch_render_plain(c->d_vox, d_tables + i * tstride, passes[i], c->shard, c->d_accum, cnt, c->stream);
+      }
       if (e != cudaSuccess) return cuda_fail(c, e, "render kernel launch");
       c->stats.kernel_launches += 1;
       c->stats.render_launches += 1;
     }
   } else {
+    int warp_blocks = 0;
+    if (c->kernel_kind == 2) {  // resolved before any lock or event is taken
+      const int variant = cnt ? 1 : 0;
+      if (!c->warp_blocks[variant]) c->warp_blocks[variant] = rm_warp_blocks_per_sm(variant);
+      if (c->warp_blocks[variant] <= 0) return fail(c, RM_ERR_CUDA, "warp render kernel does not fit on an SM");
+      warp_blocks = c->warp_blocks[variant];
+    }
     int i = 0;
     while (i < n) {
       int m = 1;
       while (i + m < n && m < c->fuse_limit && fusable(passes[i], passes[i + m])) ++m;
+      if (c->kernel_kind == 0) m = rm_persist_pick_passes(m);
       int rc = ensure_accel(c, passes[i].isoVal);
       if (rc) return rc;
-      if (m > 1) {
+      if (m > 1 && c->kernel_kind != 0) {
         const size_t need = (size_t)m * (size_t)c->shard.slots;
         if (need > c->colour_capacity) {
           RM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -283,31 +332,37 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
       }
       float times[RM_MAX_FUSED_PASSES], blend[RM_MAX_FUSED_PASSES];
       for (int k = 0; k < m; ++k) { times[k] = passes[i + k].time; blend[k] = passes[i + k].frameBlend; }
-      EventPair t = begin_timed(c, 0);
       cudaError_t e;
-      guard_before_launch(c);
-      if (c->kernel_kind == 2) {
-        const int variant = cnt ? 1 : 0;
-        if (!c->warp_blocks[variant]) c->warp_blocks[variant] = rm_warp_blocks_per_sm(variant);
-        if (c->warp_blocks[variant] <= 0) return fail(c, RM_ERR_CUDA, "warp render kernel does not fit on an SM");
-        e = rm_launch_render_warp(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, m, c->d_colour,
-                                  c->d_accum, c->d_queue, cnt, c->d_watchdog, c->trip_limit,
-                                  c->warp_blocks[variant] * c->num_sms, c->stream);
-        if (e == cudaSuccess && m > 1)
-          e = rm_launch_blend_passes(c->d_colour, blend, m, c->shard, c->W, c->H, c->d_accum, c->stream);
-      } else if (c->kernel_kind == 3 && rm_wave_supports(passes[i])) {
-        int launched = 0;
-        e = rm_launch_render_wave(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
-                                  c->d_colour, c->d_accum, cnt, &c->wave, c->num_sms, c->wave_chunk, c->wave_refill, &launched, c->stream);
-        c->stats.kernel_launches += launched - (m > 1 ? 2 : 1);  // (the common bookkeeping below adds that much)
-      } else {
-        e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
-                                  c->d_colour, c->d_accum, cnt, c->stream);
+      int launched = m > 1 ? 2 : 1;
+      {
+        LaunchScope scope(c);
+        if (c->kernel_kind == 2) {
+          e = rm_launch_render_warp(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, m, c->d_colour,
+                                    c->d_accum, c->d_queue, cnt, c->d_watchdog, c->trip_limit, warp_blocks * c->num_sms, c->stream);
+          if (e == cudaSuccess && m > 1)
+            e = rm_launch_blend_passes(c->d_colour, blend, m, c->shard, c->W, c->H, c->d_accum, c->stream);
+        } else if (c->kernel_kind == 3 && rm_wave_supports(passes[i])) {
+          launched = 0;
+          e = rm_launch_render_wave(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
+                                    c->d_colour, c->d_accum, cnt, &c->wave, c->num_sms, c->wave_chunk, c->wave_refill, &launched, c->stream);
+        } else if (c->kernel_kind == 0) {
+          int packed = 0;
+          uint32_t* argb = fused_argb_target(c, &packed);
+          e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
+                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, c->persist_block, c->stream);
+          launched = 1;
+          if (e == cudaSuccess && argb) {
+            c->argb_fresh_ptr = argb;
+            c->argb_fresh_packed = packed;
+            c->argb_fresh_gamma = passes[i].gamma;
+          }
+        } else {
+          e = rm_launch_render_fast(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m,
+                                    c->d_colour, c->d_accum, cnt, c->stream);
+        }
       }
-      guard_after_launch(c);
-      end_timed(c, t);
       if (e != cudaSuccess) return cuda_fail(c, e, "render kernel launch");
-      c->stats.kernel_launches += m > 1 ? 2 : 1;
+      c->stats.kernel_launches += launched;
       c->stats.render_launches += 1;
       i += m;
     }
@@ -333,8 +388,30 @@ int check_watchdog(rm_ctx* c) {
   return fail(c, RM_ERR_CUDA, msg);
 }
 
+// Make room for a volume of `bytes` bytes that is about to be (re)written. From here until
+// commit_volume() the context has no usable volume: the occupancy data is invalid and the extents
+// are cleared, so a failure half way leaves nothing stale behind (a render then fails with
+// RM_ERR_NO_VOLUME / RM_ERR_BAD_OPTS instead of reading freed or half-written memory).
+int begin_volume(rm_ctx* c, size_t bytes, const char* who) {
+  if (bytes / 64 > 0x7fffffffULL) return fail(c, RM_ERR_INVALID_ARG, std::string(who) + ": more than 2^37 voxels");
+  c->accel.valid = false;
+  c->rx = c->ry = c->rz = 0;
+  if (bytes > c->vox_capacity) {  // the allocation is kept across re-uploads (the reference re-uploads every frame)
+    RM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
+    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
+    c->vox_capacity = bytes;
+  }
+  return RM_OK;
+}
+
+void commit_volume(rm_ctx* c, int rx, int ry, int rz) {
+  c->rx = rx; c->ry = ry; c->rz = rz;
+  c->accel.valid = false;
+}
+
 int require_ready(rm_ctx* c) {
-  if (!c->d_vox) return fail(c, RM_ERR_NO_VOLUME, "no volume uploaded (rm_set_volume)");
+  if (!c->d_vox || c->rx <= 0) return fail(c, RM_ERR_NO_VOLUME, "no volume uploaded (rm_set_volume)");
   if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
   return RM_OK;
 }
@@ -378,12 +455,18 @@ int rm_create(int device_id, rm_ctx** out_ctx) {
       (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMalloc(&c->d_counters, sizeof(RmCounters))) != cudaSuccess ||
       (e = cudaMemset(c->d_counters, 0, sizeof(RmCounters))) != cudaSuccess ||
-      (e = cudaMalloc(&c->d_queue, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_queue, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(c->d_queue, 0, 2 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMalloc(&c->d_watchdog, 16 * sizeof(unsigned))) != cudaSuccess ||
       (e = cudaMemset(c->d_watchdog, 0, 16 * sizeof(unsigned))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "rm_create");
-    delete c;
+    rm_destroy(c);
     return rc;
+  }
+  for (int b = 0; b < 2; ++b) {
+    cudaEventCreateWithFlags(&c->frame_ready[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->copy_done[b], cudaEventDisableTiming);
   }
   c->stream = c->own_stream;
   c->num_sms = prop.multiProcessorCount;
@@ -396,11 +479,16 @@ void rm_destroy(rm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (int b = 0; b < 2; ++b) {
+    if (c->frame_ready[b]) cudaEventDestroy(c->frame_ready[b]);
+    if (c->copy_done[b]) cudaEventDestroy(c->copy_done[b]);
+  }
   guard_forget(c);
   if (c->launch_done) cudaEventDestroy(c->launch_done);
   resolve_timers(c);
   for (EventPair& p : c->free_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
-  cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_tables); cudaFree(c->d_counters);
+  cudaFree(c->d_vox); cudaFree(c->d_accum); cudaFree(c->d_argb2[0]); cudaFree(c->d_argb2[1]); cudaFree(c->d_tables); cudaFree(c->d_counters);
   cudaFree(c->d_colour); cudaFree(c->d_queue); cudaFree(c->d_watchdog);
   rm_wave_free(&c->wave);
   rm_accel_free(&c->accel);
@@ -414,21 +502,30 @@ int rm_set_volume(rm_ctx* c, const uint8_t* voxels, int rx, int ry, int rz) {
   if ((long long)rx * ry > 0x7fffffffLL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: rx*ry overflows int (voxelRes.w)");
   RM_CUDA(c, cudaSetDevice(c->device));
   const size_t bytes = (size_t)rx * ry * rz;
-  if (bytes / 64 > 0x7fffffffULL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: more than 2^37 voxels");
-  if (bytes > c->vox_capacity) {  // the allocation is kept across re-uploads (the reference re-uploads every frame)
-    RM_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
-    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
-    c->vox_capacity = bytes;
-  }
+  int rc = begin_volume(c, bytes, "rm_set_volume");
+  if (rc) return rc;
   EventPair t = begin_timed(c, 2);
   cudaError_t e = cudaMemcpyAsync(c->d_vox, voxels, bytes, cudaMemcpyHostToDevice, c->stream);
   end_timed(c, t);
   if (e != cudaSuccess) return cuda_fail(c, e, "volume upload");
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stats.h2d_bytes += bytes;
-  c->rx = rx; c->ry = ry; c->rz = rz;
-  c->accel.valid = false;
+  commit_volume(c, rx, ry, rz);
+  return RM_OK;
+}
+
+// The same from DEVICE memory (e.g. a volume assembled by an all-gather over NVLink, or produced by
+// another kernel): one device-to-device copy on the context's stream, no host traffic.
+int rm_set_volume_device(rm_ctx* c, const void* d_voxels, int rx, int ry, int rz) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!d_voxels || rx <= 0 || ry <= 0 || rz <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume_device: null volume or non-positive extent");
+  if ((long long)rx * ry > 0x7fffffffLL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume_device: rx*ry overflows int (voxelRes.w)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)rx * ry * rz;
+  int rc = begin_volume(c, bytes, "rm_set_volume_device");
+  if (rc) return rc;
+  RM_CUDA(c, cudaMemcpyAsync(c->d_vox, d_voxels, bytes, cudaMemcpyDefault, c->stream));
+  commit_volume(c, rx, ry, rz);
   return RM_OK;
 }
 
@@ -478,13 +575,8 @@ int rm_generate_gyroid_volume(rm_ctx* c, int rx, int ry, int rz) {
     return fail(c, RM_ERR_INVALID_ARG, "rm_generate_gyroid_volume: bad extents");
   RM_CUDA(c, cudaSetDevice(c->device));
   const size_t bytes = (size_t)rx * ry * rz;
-  if (bytes / 64 > 0x7fffffffULL) return fail(c, RM_ERR_INVALID_ARG, "rm_generate_gyroid_volume: more than 2^37 voxels");
-  if (bytes > c->vox_capacity) {
-    RM_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
-    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
-    c->vox_capacity = bytes;
-  }
+  int rc = begin_volume(c, bytes, "rm_generate_gyroid_volume");
+  if (rc) return rc;
   double* d_trig = nullptr;
   RM_CUDA(c, cudaMalloc(&d_trig, sizeof(double) * 2 * ((size_t)rx + ry + rz)));
   cudaError_t e = rm_launch_gyroid(rx, ry, rz, d_trig, c->d_vox, c->stream);
@@ -492,8 +584,7 @@ int rm_generate_gyroid_volume(rm_ctx* c, int rx, int ry, int rz) {
   cudaFree(d_trig);
   if (e != cudaSuccess) return cuda_fail(c, e, "gyroid generator");
   c->stats.kernel_launches += 4;
-  c->rx = rx; c->ry = ry; c->rz = rz;
-  c->accel.valid = false;
+  commit_volume(c, rx, ry, rz);
   return RM_OK;
 }
 
@@ -504,13 +595,8 @@ int rm_generate_terrain_volume(rm_ctx* c, int rx, int ry, int rz) {
     return fail(c, RM_ERR_INVALID_ARG, "rm_generate_terrain_volume: bad extents");
   RM_CUDA(c, cudaSetDevice(c->device));
   const size_t bytes = (size_t)rx * ry * rz;
-  if (bytes / 64 > 0x7fffffffULL) return fail(c, RM_ERR_INVALID_ARG, "rm_generate_terrain_volume: more than 2^37 voxels");
-  if (bytes > c->vox_capacity) {
-    RM_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
-    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
-    c->vox_capacity = bytes;
-  }
+  int rc = begin_volume(c, bytes, "rm_generate_terrain_volume");
+  if (rc) return rc;
   double* d_trig = nullptr;
   RM_CUDA(c, cudaMalloc(&d_trig, sizeof(double) * 2 * ((size_t)rx + ry + rz)));
   cudaError_t e = rm_launch_terrain(rx, ry, rz, d_trig, c->d_vox, c->stream);
@@ -518,8 +604,7 @@ int rm_generate_terrain_volume(rm_ctx* c, int rx, int ry, int rz) {
   cudaFree(d_trig);
   if (e != cudaSuccess) return cuda_fail(c, e, "terrain generator");
   c->stats.kernel_launches += 3;
-  c->rx = rx; c->ry = ry; c->rz = rz;
-  c->accel.valid = false;
+  commit_volume(c, rx, ry, rz);
   return RM_OK;
 }
 
@@ -530,14 +615,13 @@ int rm_voxelize_points(rm_ctx* c, const float* xyz, int64_t n_points, int res, i
   if (!c) return RM_ERR_INVALID_ARG;
   if (!xyz || n_points <= 0 || n_points > (1ll << 40)) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: null points or bad count");
   if (res <= 0 || res > 2048 || ks > 64) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: res must be 1..2048 and ks <= 64");
+  // the splat kernel runs one thread per (point, x-offset of the dilation cube): its 256-thread block count must fit a grid
+  if ((long long)n_points * (2 * (ks < 0 ? 0 : ks) + 1) > 256ll * 0x7fffffffLL)
+    return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: n_points * (2*ks + 1) exceeds 2^39 splat threads");
   RM_CUDA(c, cudaSetDevice(c->device));
   const size_t bytes = (size_t)res * res * res;
-  if (bytes > c->vox_capacity) {
-    RM_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->d_vox) { cudaFree(c->d_vox); c->d_vox = nullptr; c->vox_capacity = 0; }
-    RM_CUDA(c, cudaMalloc(&c->d_vox, bytes));
-    c->vox_capacity = bytes;
-  }
+  int rc = begin_volume(c, bytes, "rm_voxelize_points");
+  if (rc) return rc;
   float* d_xyz = nullptr;
   int* d_bb = nullptr;
   const size_t pbytes = (size_t)n_points * 3 * sizeof(float);
@@ -550,9 +634,8 @@ int rm_voxelize_points(rm_ctx* c, const float* xyz, int64_t n_points, int res, i
   cudaFree(d_xyz);
   cudaFree(d_bb);
   if (e != cudaSuccess) return cuda_fail(c, e, "point voxeliser");
-  c->rx = c->ry = c->rz = res;
-  c->accel.valid = false;
   if (bad) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: NaN or infinite coordinate");
+  commit_volume(c, res, res, res);
   c->stats.h2d_bytes += pbytes;
   c->stats.kernel_launches += 2;
   return RM_OK;
@@ -562,7 +645,7 @@ int rm_voxelize_points(rm_ctx* c, const float* xyz, int64_t n_points, int res, i
 int rm_read_volume(rm_ctx* c, uint8_t* voxels_out) {
   if (!c) return RM_ERR_INVALID_ARG;
   if (!voxels_out) return fail(c, RM_ERR_INVALID_ARG, "rm_read_volume: null output");
-  if (!c->d_vox) return fail(c, RM_ERR_NO_VOLUME, "no volume uploaded (rm_set_volume)");
+  if (!c->d_vox || c->rx <= 0) return fail(c, RM_ERR_NO_VOLUME, "no volume uploaded (rm_set_volume)");
   RM_CUDA(c, cudaSetDevice(c->device));
   const size_t bytes = (size_t)c->rx * c->ry * c->rz;
   RM_CUDA(c, cudaMemcpyAsync(voxels_out, c->d_vox, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -596,13 +679,16 @@ int rm_clear_accum(rm_ctx* c, int width, int height) {
   const size_t n = (size_t)width * height;
   if (n > c->fb_capacity) {
     RM_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_accum); cudaFree(c->d_argb);
-    c->d_accum = nullptr; c->d_argb = nullptr; c->fb_capacity = 0;
+    if (c->copy_stream) RM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    cudaFree(c->d_accum); cudaFree(c->d_argb2[0]); cudaFree(c->d_argb2[1]);
+    c->d_accum = nullptr; c->d_argb2[0] = c->d_argb2[1] = nullptr; c->fb_capacity = 0;
     RM_CUDA(c, cudaMalloc(&c->d_accum, n * sizeof(float4)));
-    RM_CUDA(c, cudaMalloc(&c->d_argb, n * sizeof(uint32_t)));
+    RM_CUDA(c, cudaMalloc(&c->d_argb2[0], n * sizeof(uint32_t)));
+    RM_CUDA(c, cudaMalloc(&c->d_argb2[1], n * sizeof(uint32_t)));
     c->fb_capacity = n;
   }
   c->W = width; c->H = height;
+  c->argb_fresh_ptr = nullptr;
   update_shard(c);
   RM_CUDA(c, cudaMemsetAsync(c->d_accum, 0, n * sizeof(float4), c->stream));
   return RM_OK;
@@ -632,8 +718,10 @@ int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, 
   }
   const size_t tbytes = (size_t)RM_TABLE_FLOATS * sizeof(float);
   if ((rc = ensure_tables(c, iter > c->resident ? iter : c->resident))) return rc;
-  // a frame rendered from host buffers replaces any resident passes
+  // a frame rendered from host buffers replaces any resident passes and overwrites table slots
+  // 0 .. iter-1, including tables generated in place (rm_generate_scatter_tables)
   c->resident = 0;
+  c->generated_tables = 0;
   EventPair t = begin_timed(c, 2);
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < iter && e == cudaSuccess; ++i)  // straight from the caller's (ideally pinned) buffers
@@ -677,6 +765,26 @@ int rm_upload_passes(rm_ctx* c, const void* const* opts, const float* const* mc,
   return RM_OK;
 }
 
+// update-render-option-buffer (core.clj:108-117) for resident passes: replace the opts of the `iter`
+// uploaded passes (a new camera, say); the tables stay where they are. 544 bytes per pass of host traffic.
+int rm_update_opts(rm_ctx* c, const void* const* opts, int iter) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!opts || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_update_opts: null opts array or iter <= 0");
+  if (iter != c->resident) return fail(c, RM_ERR_INVALID_ARG, "rm_update_opts: iter differs from the passes uploaded by rm_upload_passes");
+  int rc = require_ready(c);
+  if (rc) return rc;
+  std::vector<RmOpts> dec((size_t)iter);
+  for (int i = 0; i < iter; ++i) {
+    if (!opts[i]) return fail(c, RM_ERR_INVALID_ARG, "rm_update_opts: null per-pass pointer");
+    std::memset(&dec[i], 0, sizeof(RmOpts));
+    decode_opts(opts[i], &dec[i]);
+    if ((rc = check_opts(c, dec[i]))) return rc;
+  }
+  c->passes = dec;
+  c->stats.h2d_bytes += (size_t)RM_OPTS_BYTES * iter;
+  return RM_OK;
+}
+
 int rm_render_resident(rm_ctx* c, int first, int count) {
   if (!c) return RM_ERR_INVALID_ARG;
   int rc = require_ready(c);
@@ -689,6 +797,25 @@ int rm_render_resident(rm_ctx* c, int first, int count) {
   return launch_passes(c, c->passes.data() + first, count, c->d_tables + (size_t)first * (RM_TABLE_FLOATS / 4));
 }
 
+// Is `buf` (indexed like `packed` says) already tonemap(accumulator, gamma)? True when the default
+// kernel wrote it while rendering the last launch and nothing has touched the accumulator since.
+static bool argb_is_fresh(const rm_ctx* c, const void* buf, int packed, float gamma) {
+  return c->argb_fresh_ptr && c->argb_fresh_ptr == buf && (c->argb_fresh_packed != 0) == (packed != 0) &&
+         std::memcmp(&c->argb_fresh_gamma, &gamma, sizeof(float)) == 0;
+}
+
+// TonemapImage into the context's current ARGB frame (skipped when the render launch already wrote it).
+static int tonemap_into_frame(rm_ctx* c, const RmOpts& o) {
+  uint32_t* frame = c->d_argb2[c->argb_cur];
+  if (argb_is_fresh(c, frame, 0, o.gamma)) return RM_OK;
+  EventPair t = begin_timed(c, 1);
+  cudaError_t e = rm_launch_tonemap(c->d_accum, o.gamma, c->W, c->H, c->shard, frame, 0, c->stream);
+  end_timed(c, t);
+  if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
+  c->stats.kernel_launches += 1;
+  return RM_OK;
+}
+
 int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out) {
   if (!c) return RM_ERR_INVALID_ARG;
   if (!opts || opts_len != RM_OPTS_BYTES || !argb_out) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap: bad opts blob or null output");
@@ -698,19 +825,82 @@ int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out)
   decode_opts(opts, &o);
   if (o.width != c->W || o.height != c->H) return fail(c, RM_ERR_BAD_OPTS, "rm_tonemap: TRenderOpts.resolution does not match the framebuffer");
   const size_t n = (size_t)c->W * c->H;
-  int rc;
-  EventPair t = begin_timed(c, 1);
-  cudaError_t e = rm_launch_tonemap(c->d_accum, o.gamma, c->W, c->H, c->shard, c->d_argb, 0, c->stream);
-  end_timed(c, t);
-  if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
-  c->stats.kernel_launches += 1;
+  int rc = tonemap_into_frame(c, o);
+  if (rc) return rc;
   EventPair t2 = begin_timed(c, 3);
-  e = cudaMemcpyAsync(argb_out, c->d_argb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaMemcpyAsync(argb_out, c->d_argb2[c->argb_cur], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   end_timed(c, t2);
   if (e != cudaSuccess) return cuda_fail(c, e, "argb read-back");
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   if ((rc = check_watchdog(c))) return rc;
   c->stats.d2h_bytes += n * sizeof(uint32_t);
+  return RM_OK;
+}
+
+// TonemapImage + an ASYNCHRONOUS read-back into (ideally pinned) host memory: returns as soon as the
+// work is queued. The copy runs on a second stream out of one of two ARGB frames, so the next frame
+// (rm_clear_accum / rm_render_* after this call) renders into the other one while this one travels.
+// slot (0 or 1) names the transfer for rm_wait.
+int rm_tonemap_async(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out, int slot) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!opts || opts_len != RM_OPTS_BYTES || !argb_out) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap_async: bad opts blob or null output");
+  if (slot < 0 || slot > 1) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap_async: slot must be 0 or 1");
+  if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RmOpts o;
+  decode_opts(opts, &o);
+  if (o.width != c->W || o.height != c->H) return fail(c, RM_ERR_BAD_OPTS, "rm_tonemap_async: TRenderOpts.resolution does not match the framebuffer");
+  if (c->copy_pending[slot]) {  // the caller reuses a slot it never waited for
+    RM_CUDA(c, cudaEventSynchronize(c->copy_done[c->slot_buffer[slot]]));
+    c->copy_pending[slot] = false;
+  }
+  int rc = tonemap_into_frame(c, o);
+  if (rc) return rc;
+  const int b = c->argb_cur;
+  const size_t n = (size_t)c->W * c->H;
+  RM_CUDA(c, cudaEventRecord(c->frame_ready[b], c->stream));
+  RM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->frame_ready[b], 0));
+  RM_CUDA(c, cudaMemcpyAsync(argb_out, c->d_argb2[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+  RM_CUDA(c, cudaEventRecord(c->copy_done[b], c->copy_stream));
+  c->copy_pending[slot] = true;
+  c->slot_buffer[slot] = b;
+  c->stats.d2h_bytes += n * sizeof(uint32_t);
+  // the next frame goes to the other buffer -- once the transfer that last used it has drained
+  c->argb_cur = b ^ 1;
+  c->argb_fresh_ptr = nullptr;
+  for (int s2 = 0; s2 < 2; ++s2)
+    if (c->copy_pending[s2] && c->slot_buffer[s2] == c->argb_cur)
+      RM_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[c->argb_cur], 0));
+  return RM_OK;
+}
+
+// Block until the transfer started by rm_tonemap_async(.., slot) has landed in host memory.
+int rm_wait(rm_ctx* c, int slot) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (slot < 0 || slot > 1) return fail(c, RM_ERR_INVALID_ARG, "rm_wait: slot must be 0 or 1");
+  if (!c->copy_pending[slot]) return RM_OK;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RM_CUDA(c, cudaEventSynchronize(c->copy_done[c->slot_buffer[slot]]));
+  c->copy_pending[slot] = false;
+  return check_watchdog(c);
+}
+
+int rm_host_alloc(rm_ctx* c, size_t bytes, void** out_ptr) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!out_ptr || bytes == 0) return fail(c, RM_ERR_INVALID_ARG, "rm_host_alloc: null out pointer or zero size");
+  *out_ptr = nullptr;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  RM_CUDA(c, cudaHostAlloc(out_ptr, bytes, cudaHostAllocPortable));
+  return RM_OK;
+}
+
+int rm_host_free(rm_ctx* c, void* ptr) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (!ptr) return RM_OK;
+  RM_CUDA(c, cudaSetDevice(c->device));
+  for (int s2 = 0; s2 < 2; ++s2)  // a transfer into it may still be in flight
+    if (c->copy_pending[s2]) { cudaEventSynchronize(c->copy_done[c->slot_buffer[s2]]); c->copy_pending[s2] = false; }
+  RM_CUDA(c, cudaFreeHost(ptr));
   return RM_OK;
 }
 
@@ -722,11 +912,25 @@ int rm_tonemap_device(rm_ctx* c, const void* opts, size_t opts_len, void* d_argb
   RmOpts o;
   decode_opts(opts, &o);
   if (o.width != c->W || o.height != c->H) return fail(c, RM_ERR_BAD_OPTS, "rm_tonemap_device: TRenderOpts.resolution does not match the framebuffer");
+  if (argb_is_fresh(c, d_argb, packed, o.gamma)) return RM_OK;  // the render launch wrote it (rm_set_argb_target)
   EventPair t = begin_timed(c, 1);
   cudaError_t e = rm_launch_tonemap(c->d_accum, o.gamma, c->W, c->H, c->shard, static_cast<uint32_t*>(d_argb), packed, c->stream);
   end_timed(c, t);
   if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
   c->stats.kernel_launches += 1;
+  return RM_OK;
+}
+
+// Register a device buffer the caller owns (width*height words, or rm_shard_slots words when packed)
+// as the place where the default render kernel leaves the ARGB words of the frame while it renders:
+// a later rm_tonemap_device(opts, same buffer, same packing) with the same gamma is then free. The
+// buffer may live on a PEER device (NVLink): every GPU of a box can store its tiles straight into
+// one frame. NULL restores the context's own frame.
+int rm_set_argb_target(rm_ctx* c, void* d_argb, int packed) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  c->argb_target = static_cast<uint32_t*>(d_argb);
+  c->argb_target_packed = d_argb ? (packed != 0) : 0;
+  c->argb_fresh_ptr = nullptr;
   return RM_OK;
 }
 
@@ -778,6 +982,7 @@ int rm_set_tile_shard(rm_ctx* c, int rank, int world, int tile_w, int tile_h) {
   if (world <= 0 || rank < 0 || rank >= world || tile_w <= 0 || tile_h <= 0 || (tile_w & 7) || (tile_h & 3))
     return fail(c, RM_ERR_INVALID_ARG, "rm_set_tile_shard: need 0 <= rank < world, tile_w % 8 == 0, tile_h % 4 == 0");
   c->shard_rank = rank; c->shard_world = world; c->shard_tw = tile_w; c->shard_th = tile_h;
+  c->argb_fresh_ptr = nullptr;
   update_shard(c);
   return RM_OK;
 }
@@ -822,7 +1027,7 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
   switch (option) {
     case RM_OPT_COUNT_WORK: c->count_work = value != 0; return RM_OK;
     case RM_OPT_KERNEL:
-      if (value < 0 || value > 3) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_KERNEL: 0 (bricks), 1 (plain), 2 (warp) or 3 (wavefront)");
+      if (value < 0 || value > 4) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_KERNEL: 0 (persistent, default), 1 (plain), 2 (warp), 3 (wavefront) or 4 (per-item bricks)");
       c->kernel_kind = (int)value;
       return RM_OK;
     case RM_OPT_CELL_SHIFT:
@@ -841,6 +1046,11 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
     case RM_OPT_TRIP_LIMIT:
       if (value < 1 || value > 0xffffffffLL) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_TRIP_LIMIT: 1..2^32-1");
       c->trip_limit = (unsigned)value;
+      return RM_OK;
+    case RM_OPT_PERSIST_BLOCK:
+      if (value != 0 && value != 512 && value != 768 && value != 1024)
+        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 512, 768 or 1024 threads");
+      c->persist_block = (int)value;
       return RM_OK;
     case RM_OPT_FUSE_LIMIT:
       if (value < 1 || value > RM_MAX_FUSED_PASSES) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_FUSE_LIMIT: 1..32");

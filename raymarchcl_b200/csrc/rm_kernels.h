@@ -61,6 +61,23 @@ cudaError_t rm_launch_render_fast(const RmOpts& opts, const RmShard& shard, cons
 cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, int passes, const RmShard& shard,
                                    int W, int H, float4* d_accum, cudaStream_t stream);
 
+// ---- default kernel: persistent warps, distance map in shared memory, blend + tonemap folded in
+// (rm_scene_fused.cuh, rm_render_persist.cu), RM_OPT_KERNEL = 0 ----
+#define RM_PERSIST_MAX_SMEM (200 * 1024) // largest 4-bit distance map staged into shared memory
+// How many of `available` consecutive fusable passes one launch should take: all (<= 32) when they
+// fill >= 80 % of a warp's lanes as whole pixels x passes groups, else the largest power of two.
+int rm_persist_pick_passes(int available);
+// RenderImage for `passes` consecutive fusable passes, blended into d_accum in pass order inside the
+// kernel. d_argb (optional): the ARGB words of the frame so far (TonemapImage with opts.gamma), indexed
+// by pixel id or, argb_packed != 0, by shard slot (padding slots = 0). d_queue: one 64-bit ticket
+// counter owned by the context, *queue_base its expected value (updated by this call; never reset).
+// block_threads: 512 / 768 / 1024 threads of the one resident block per SM (128 / 80 / 64 registers).
+cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
+                                     const float4* d_tables, const float* times, const float* blend, int passes,
+                                     float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
+                                     unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
+                                     int block_threads, cudaStream_t stream);
+
 // ---- warp-scheduled state machine (rm_render_warp.cu), RM_OPT_KERNEL = 2 ----
 int rm_warp_blocks_per_sm(int count);
 // Persistent launch over (pixel, pass) items; colours go to d_colour when passes > 1 (blend with

@@ -1,0 +1,230 @@
+// rm_render_persist.cu -- the DEFAULT RenderImage kernel (renderer.cl:478-494) for sm_100a, with
+// the frame's blend (renderer.cl:492) and TonemapImage (renderer.cl:496-508) folded into it.
+//
+//   persistent   one 1024-thread block per SM for the whole launch. Each WARP takes the next bundle
+//                of 32 work items from a global ticket counter when all its lanes are done: no block
+//                ever waits for its slowest warp (the per-item kernel lost 15 % of its warp slots to
+//                that: 52.9 % active of a possible 62.5 %), and because the same threads keep the same
+//                registers there is nothing left in local memory to write back.
+//   bundles      a bundle is 32 / m neighbouring pixels x the m passes of the launch, pass-minor:
+//                the lanes of a warp render the SAME pixels in different passes (rays that differ
+//                only by jitter), which is what keeps their control flow together.
+//   TMA          on block start one thread arms an mbarrier and issues cp.async.bulk copies of the
+//                4-bit macro-cell distance map (<= 128 KiB at <= 64^3 cells) into shared memory; the
+//                march reads it with LDS (rm_scene_fused.cuh) -- its load from global memory was the
+//                top stall site of the per-item kernel (79 % long-scoreboard).
+//   blend        the m passes of a pixel sit in m adjacent lanes: mix(pixels, colour_k, frameBlend_k)
+//                is folded in pass order with warp shuffles -- the same operations in the same order
+//                as m separate RenderImage launches, hence the same bits -- and written once. No colour
+//                buffer (531 MB at C2), no blend kernel.
+//   tonemap      the lane that writes the accumulator also writes the ARGB word of the frame so far
+//                (gamma of the launch's opts); rm_tonemap returns that buffer when nothing changed.
+//
+// Compiled with -fmad=false like the rest of the library (pinned two-rounding evaluation order).
+#include <mutex>
+
+#include "rm_kernels.h"
+#include "rm_scene_fused.cuh"
+
+namespace {
+
+
+struct PersistParams {
+  const float4* tables;              // passes x 16384 float4
+  float times[RM_MAX_FUSED_PASSES];  // TRenderOpts.time per pass
+  float blend[RM_MAX_FUSED_PASSES];  // TRenderOpts.frameBlend per pass
+  float4* accum;
+  uint32_t* argb;                    // optional: TonemapImage output of the frame so far
+  float gamma;
+  int argb_packed;                   // argb is indexed by shard slot (else by pixel id)
+  RmCounters* counters;
+  unsigned long long* queue;         // bundle tickets: monotonic across launches, see rm_launch_render_persist
+  unsigned long long queue_base;
+  long long bundles;
+  int passes;                        // m
+  int ppb;                           // pixels per bundle = 32 / m
+  const uint8_t* nib;                // 4-bit distance map in global memory (source of the bulk copy)
+  unsigned nib_bytes;                // multiple of 16
+};
+
+// tonemap + pack of one pixel (renderer.cl:448-454, :502-506); same expression as rm_kernels.cu
+__device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
+  const float c[3] = {p.x, p.y, p.z};
+  uint32_t ch[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float t = c[i] / (gamma + c[i]);
+    t = t * t * 255.0f;
+    ch[i] = (uint32_t)f2i_sat(cl_clamp(t, 0.0f, 255.0f));
+  }
+  return 0xff000000u | (ch[0] << 16) | (ch[1] << 8) | ch[2];
+}
+
+// kThreads: threads of the one resident block per SM = 65536 / registers per thread. 1024 (64
+// registers, some spills in the shading code), 768 (80) and 512 (128, no spills) are compiled;
+// RM_OPT_PERSIST_BLOCK selects, the default is the measured best.
+template <bool kCount, bool kNib, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
+k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ PersistParams P) {
+  const RmOpts& o = fused::g_opts;
+  if (kNib) {
+    // Stage the distance map: bulk async copies (TMA engine, no registers, no per-thread loads)
+    // complete on an mbarrier that every thread of the block then waits on.
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(P.nib_bytes) : "memory");
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(fused::rm_smem_nib);
+      for (unsigned off = 0; off < P.nib_bytes; off += 32768u) {
+        const unsigned n = P.nib_bytes - off < 32768u ? P.nib_bytes - off : 32768u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + off), "l"(P.nib + off), "r"(n), "r"(bar) : "memory");
+      }
+    }
+    unsigned done;
+    do {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    } while (!done);
+  }
+
+  const unsigned lane = threadIdx.x & 31u;
+  const int m = P.passes;
+  const int sub = (int)lane / m, pass = (int)lane - sub * m;  // pixel of the bundle, pass of the launch
+  const bool lane_used = sub < P.ppb;
+  const int base = sub * m;  // first lane of this pixel's group
+  fused::Cnt<kCount> cnt;
+  fused::Lane s;
+  s.table = P.tables + (size_t)(lane_used ? pass : 0) * (RM_TABLE_MASK + 1);
+  s.time = P.times[lane_used ? pass : 0];
+
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(P.queue, 1ull) - P.queue_base;
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= (unsigned long long)P.bundles) break;
+    const long long slot = (long long)t * P.ppb + sub;
+    const bool in_shard = lane_used && slot < sh.slots;
+    const int id = in_shard ? rm_slot_to_pixel(sh, slot, o.width, o.height) : -1;
+    float3 c = f3s(0.0f);
+    if (id >= 0) c = fused::render_pixel_sample<kCount, kNib>(cnt, s, id);
+    __syncwarp();
+    // pixels = mix(pixels, colour_k, frameBlend_k), k = 0 .. m-1 in pass order (renderer.cl:492)
+    float3 p = f3s(0.0f);
+    if (id >= 0) {
+      const float4 old = P.accum[id];
+      p = f3(old.x, old.y, old.z);
+    }
+    for (int k = 0; k < m; ++k) {
+      const float3 ck = f3(__shfl_sync(0xffffffffu, c.x, base + k), __shfl_sync(0xffffffffu, c.y, base + k),
+                           __shfl_sync(0xffffffffu, c.z, base + k));
+      p = lerp3(p, ck, P.blend[k]);
+    }
+    if (in_shard && pass == 0) {
+      if (id >= 0) P.accum[id] = make_float4(p.x, p.y, p.z, 1.0f);
+      if (P.argb) {
+        if (P.argb_packed) P.argb[slot] = id >= 0 ? tonemap_pack3(p, P.gamma) : 0u;
+        else if (id >= 0) P.argb[id] = tonemap_pack3(p, P.gamma);
+      }
+    }
+  }
+
+  if constexpr (kCount) {
+    unsigned long long a = cnt.steps, b = cnt.taps, c = cnt.outer;
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, off);
+      b += __shfl_down_sync(0xffffffffu, b, off);
+      c += __shfl_down_sync(0xffffffffu, c, off);
+    }
+    if (lane == 0) {
+      atomicAdd(&P.counters->steps, a);
+      atomicAdd(&P.counters->taps, b);
+      atomicAdd(&P.counters->outer, c);
+    }
+  }
+}
+
+// function attributes are per device: set once per (device, instantiation)
+std::once_flag g_attr_once[64][16];
+
+template <bool kCount, bool kNib, int kThreads>
+cudaError_t launch(const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev, cudaStream_t stream) {
+  cudaError_t attr = cudaSuccess;
+  constexpr int variant = ((kThreads / 256 - 1) << 2) | (kCount ? 2 : 0) | (kNib ? 1 : 0);
+  std::call_once(g_attr_once[dev & 63][variant], [&] {
+    if (kNib) attr = cudaFuncSetAttribute(k_render_persist<kCount, kNib, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PERSIST_MAX_SMEM);
+    else attr = cudaFuncSetAttribute(k_render_persist<kCount, kNib, kThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  });
+  if (attr != cudaSuccess) return attr;
+  k_render_persist<kCount, kNib, kThreads><<<blocks, kThreads, smem, stream>>>(shard, P);
+  return cudaGetLastError();
+}
+
+template <bool kNib>
+cudaError_t launch_any(bool count, int threads, const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev,
+                       cudaStream_t stream) {
+  if (count) return launch<true, kNib, 1024>(shard, P, blocks, smem, dev, stream);
+  if (threads == 512) return launch<false, kNib, 512>(shard, P, blocks, smem, dev, stream);
+  if (threads == 768) return launch<false, kNib, 768>(shard, P, blocks, smem, dev, stream);
+  return launch<false, kNib, 1024>(shard, P, blocks, smem, dev, stream);
+}
+
+}  // namespace
+
+int rm_persist_pick_passes(int available) {
+  int m = available < RM_MAX_FUSED_PASSES ? available : RM_MAX_FUSED_PASSES;
+  if (m < 1) return 0;
+  if ((32 / m) * m * 5 >= 32 * 4) return m;  // >= 80 % of the lanes carry an item
+  int p = 1;
+  while (p * 2 <= m) p *= 2;
+  return p;
+}
+
+cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
+                                     const float4* d_tables, const float* times, const float* blend, int passes,
+                                     float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
+                                     unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
+                                     int block_threads, cudaStream_t stream) {
+  if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
+  if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
+  PersistParams P;
+  P.tables = d_tables;
+  for (int i = 0; i < RM_MAX_FUSED_PASSES; ++i) {
+    P.times[i] = i < passes ? times[i] : 0.0f;
+    P.blend[i] = i < passes ? blend[i] : 0.0f;
+  }
+  P.accum = d_accum;
+  P.argb = d_argb;
+  P.gamma = opts.gamma;
+  P.argb_packed = argb_packed;
+  P.counters = d_counters;
+  P.queue = d_queue;
+  P.queue_base = *queue_base;
+  P.passes = passes;
+  P.ppb = 32 / passes;
+  P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
+  P.nib = accel.nib;
+  P.nib_bytes = accel.nib_bytes;
+  const bool use_nib = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= RM_PERSIST_MAX_SMEM;
+  const int threads = d_counters ? 1024 : (block_threads == 512 || block_threads == 768 ? block_threads : 1024);
+  const int warps_per_block = threads / 32;
+  long long blocks = (P.bundles + warps_per_block - 1) / warps_per_block;
+  if (blocks > num_sms) blocks = num_sms;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbolAsync(fused::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbolAsync(fused::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+  const size_t smem = use_nib ? accel.nib_bytes : 0;
+  e = use_nib ? launch_any<true>(d_counters != nullptr, threads, shard, P, (int)blocks, smem, dev, stream)
+              : launch_any<false>(d_counters != nullptr, threads, shard, P, (int)blocks, smem, dev, stream);
+  if (e != cudaSuccess) return e;
+  // every warp of the grid draws tickets until it draws one past the end: exactly one per warp
+  *queue_base += (unsigned long long)P.bundles + (unsigned long long)blocks * warps_per_block;
+  return cudaSuccess;
+}

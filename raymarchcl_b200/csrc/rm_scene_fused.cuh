@@ -1,0 +1,575 @@
+// rm_scene_fused.cuh -- the render op (RenderImage, renderer.cl:478-494 and its call tree) as the
+// per-pixel-sample routine of the DEFAULT kernel (rm_render_persist.cu, RM_OPT_KERNEL = 0).
+//
+// Same arithmetic, same order of operations and the same exact shortcuts as rm_scene_plain.cuh
+// (fetch elision over bit-bricks + a macro-cell Chebyshev distance map, lazy normals, slab-test
+// shortcuts, irrelevance culling, march windows, early misses; the proofs are written out there and
+// are not repeated here) -- what differs is how the routine sits on the machine:
+//
+//   * every shared (non-inlined) function takes and returns VALUES. nvcc passes them in registers,
+//     so the routine has no call stack at all (ptxas: 0 bytes stack frame); the by-reference
+//     Isec / Scene / JobResult / PixelState of rm_scene_plain.cuh cost 416 bytes of local memory per
+//     thread, ~10 % of the executed instructions and 8.5 GB of DRAM write-backs per C2 frame;
+//   * the distance map is read from SHARED MEMORY: 4 bits per macro-cell (Chebyshev distance
+//     saturated at 15), staged once per resident block with a bulk TMA copy (cp.async.bulk +
+//     mbarrier, rm_render_persist.cu). At <= 64^3 cells that is <= 128 KiB. kNib == false reads the
+//     byte map from global memory instead (grids whose map does not fit the SM).
+//
+// tests/hostsim compiles this header for the host (RM_NIB_BASE is then a plain pointer) and compares
+// the routine with the oracle bit for bit.
+#pragma once
+#include "rm_math.cuh"
+#include "rm_types.h"
+
+#ifndef RM_STAT_LOOKUP
+#define RM_STAT_LOOKUP() ((void)0)
+#define RM_STAT_SKIP(n) ((void)0)
+#define RM_STAT_JUMP(n) ((void)0)
+#define RM_STAT_SEQ(n) ((void)0)
+#define RM_STAT_MARCH() ((void)0)
+#define RM_STAT_TRACE() ((void)0)
+#define RM_STAT_EVENT(id) ((void)0)
+#endif
+#ifndef RM_STAT_SITE
+#define RM_STAT_SITE(id) ((void)0)
+#define RM_STAT_LEVEL(l) ((void)0)
+#define RM_STAT_LEVEL_GET() 0
+#endif
+
+namespace fused {
+
+// Per-launch constants in __constant__ memory (one copy per translation unit; see the note in
+// rm_scene_plain.cuh: the shared functions read them as constant-bank operands).
+static __constant__ RmOpts g_opts;
+static __constant__ RmAccel g_accel;
+
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) uint8_t rm_smem_nib[];  // the 4-bit distance map of this block
+#define RM_NIB_BASE rm_smem_nib
+#else
+static const uint8_t* rm_host_nib = nullptr;  // host simulation: the same packed map in host memory
+#define RM_NIB_BASE rm_host_nib
+#endif
+
+// Reference-equivalent work counters: a real object (by reference) in the counting kernels, an
+// empty value in the production kernels, so that those carry no address-taken local at all.
+template <bool kCount> struct Cnt {};
+template <> struct Cnt<true> { unsigned steps = 0, taps = 0, outer = 0; };
+template <bool kCount> struct CntArg { using type = Cnt<false>; };
+template <> struct CntArg<true> { using type = Cnt<true>&; };
+#define RM_CNT typename CntArg<kCount>::type
+
+struct Lane {  // what differs between the passes of one fused launch: TRenderOpts.time and the table
+  const float4* table;
+  float time;
+};
+
+struct Isec {  // TIsec, renderer.cl:6-12
+  float3 pos, normal;
+  float distance;
+  int objectID;
+};
+
+struct Hit {  // one distanceToScene call (renderer.cl:209-237) without its normal
+  float3 p;      // sample position of the solid voxel the march stopped on (when hit)
+  float dist;    // .x of the returned pair
+  bool hit;      // the march stopped on a solid voxel
+  bool closer;   // ... and the voxel distance won against the ground plane
+};
+
+RM_DEV float4 table_at(const Lane& s, uint32_t seed) { return __ldg(s.table + (seed & RM_TABLE_MASK)); }
+RM_DEV float3 table_xyz(const Lane& s, uint32_t seed) {
+  const float4 t = table_at(s, seed);
+  return f3(t.x, t.y, t.z);
+}
+
+// renderer.cl:153-161
+RM_DEV float box_entry(float3 bmin, float3 bmax, float3 p, float3 d) {
+  const float3 t0 = (bmin - p) / d;
+  const float3 t1 = (bmax - p) / d;
+  const float a = cl_max(cl_max(cl_min(t1.x, t0.x), 0.0f), cl_max(cl_min(t1.y, t0.y), cl_min(t1.z, t0.z)));
+  const float b = cl_min(cl_max(t1.x, t0.x), cl_min(cl_max(t1.y, t0.y), cl_max(t1.z, t0.z)));
+  return b > a ? a : -1.0f;
+}
+
+RM_DEV bool in_grid(int x, int y, int z) {
+  return (unsigned)x < (unsigned)g_opts.rx && (unsigned)y < (unsigned)g_opts.ry && (unsigned)z < (unsigned)g_opts.rz;
+}
+
+// ---- occupancy data (rm_accel.cu) ----------------------------------------------------------------
+RM_DEV uint64_t brick_word(const uint64_t* __restrict__ bricks, int x, int y, int z) {
+  return __ldg(bricks + (unsigned)(((z >> 2) * g_accel.by + (y >> 2)) * g_accel.bx + (x >> 2)));
+}
+RM_DEV unsigned brick_bit(int x, int y, int z) { return (x & 3) | ((y & 3) << 2) | ((z & 3) << 4); }
+RM_DEV bool solid_at(int x, int y, int z) { return (brick_word(g_accel.solid, x, y, z) >> brick_bit(x, y, z)) & 1ull; }
+// voxelLookupI (renderer.cl:172-178): v >= isoVal, 0 outside the grid
+RM_DEV int occ_at(int x, int y, int z) {
+  if (!in_grid(x, y, z)) return 0;
+  return (int)((brick_word(g_accel.occ, x, y, z) >> brick_bit(x, y, z)) & 1ull);
+}
+RM_DEV int voxel_value(int x, int y, int z) {
+  return __ldg(g_accel.vox + ((size_t)z * g_opts.rxy + (size_t)y * g_opts.rx + x));
+}
+// Chebyshev distance (in macro-cells, saturated) from the cell of voxel (x, y, z) to the nearest cell
+// that holds a solid voxel. kNib: the 4-bit copy in shared memory; else the byte map in global memory.
+template <bool kNib>
+RM_DEV int cell_dist(int x, int y, int z) {
+  const int cs = g_accel.cell_shift;
+  const unsigned c = (unsigned)(((z >> cs) * g_accel.my + (y >> cs)) * g_accel.mx + (x >> cs));
+  if (kNib) return (RM_NIB_BASE[c >> 1] >> ((c & 1u) << 2)) & 15;
+  return __ldg(g_accel.dist + c);
+}
+
+// voxelNormal (renderer.cl:180-188) as integers
+RM_DEV void gradient6_i(int x, int y, int z, int& gx, int& gy, int& gz) {
+  gx = occ_at(x - 1, y, z) - occ_at(x + 1, y, z);
+  gy = occ_at(x, y - 1, z) - occ_at(x, y + 1, z);
+  gz = occ_at(x, y, z - 1) - occ_at(x, y, z + 1);
+}
+// unit3(voxelNormal): the reference negates a float difference, so equal taps give -0.0f
+RM_DEV float3 normal_6tap(int x, int y, int z) {
+  int gx, gy, gz;
+  gradient6_i(x, y, z, gx, gy, gz);
+  return unit3(f3(-(float)(-gx), -(float)(-gy), -(float)(-gz)));
+}
+// voxelNormalSmooth (renderer.cl:190-203); the reference's float sums of 0 / +-1 are exact
+RM_DEV float3 normal_smooth(int x, int y, int z) {
+  int sx = 0, sy = 0, sz = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx)
+        if (occ_at(x + dx, y + dy, z + dz)) {
+          int gx, gy, gz;
+          gradient6_i(x + dx, y + dy, z + dz, gx, gy, gz);
+          sx += gx; sy += gy; sz += gz;
+        }
+  return unit3(f3((float)sx, (float)sy, (float)sz));
+}
+// reference-equivalent occupancy taps of one hit (counting kernels only)
+RM_DEV unsigned taps_of_hit(int x, int y, int z, bool smooth) {
+  if (!smooth) return 6u;
+  unsigned n = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) n += occ_at(x + dx, y + dy, z + dz);
+  return 27u + 6u * n;
+}
+
+// ---- the fixed-step march (renderer.cl:219-234) ----------------------------------------------------
+// Counting form: visits every sample the reference fetches (exact step counter).
+template <bool kNib>
+RM_DEV bool march_counting(Cnt<true>& c, float3& p, float3 delta, int rem, float invS) {
+  const float rxf = (float)g_opts.rx, ryf = (float)g_opts.ry, rzf = (float)g_opts.rz;
+  while (rem > 0) {
+    const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
+    c.steps++;
+    if (!in_grid(x, y, z)) return false;
+    const int d = cell_dist<kNib>(x, y, z);
+    if (d != 0) {
+      const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
+      int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
+      n = n < rem ? n : rem;
+      rem -= n;
+      for (int j = 1; j <= n; ++j) {
+        p = p + delta;
+        if (j < n) {  // the reference fetches (and counts) every one of these samples
+          c.steps++;
+          if (!in_grid(f2i_sat(p.x * rxf), f2i_sat(p.y * ryf), f2i_sat(p.z * rzf))) return false;
+        }
+      }
+    } else {
+      if (solid_at(x, y, z)) return true;
+      p = p + delta;
+      rem -= 1;
+    }
+  }
+  return false;
+}
+
+// Production form (see march_fast in rm_scene_plain.cuh for the derivation of the skip length and
+// of the XU-free conversions): samples known to be empty cost three adds each and no fetch.
+template <bool kNib>
+RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
+  RM_STAT_MARCH();
+  const float A = g_accel.cellf * invS, B = 0.25f * invS + 0.5f;  // invS <= 2000 (march_delta)
+  while (rem > 0) {
+    const int x = f2i_sat(p.x * g_accel.rxf), y = f2i_sat(p.y * g_accel.ryf), z = f2i_sat(p.z * g_accel.rzf);
+    if (!in_grid(x, y, z)) return false;
+    const int d = cell_dist<kNib>(x, y, z);
+    RM_STAT_LOOKUP();
+    RM_STAT_EVENT(d == 0 ? 13 : (d == 1 ? 14 : (d == 2 ? 15 : 16)));
+    int n = 1;  // samples consumed by this iteration: this one plus the ones known to be empty
+    if (d > 1) {
+      const float dm1 = __int_as_float(0x4b000000 | (d - 1)) - 8388608.0f;
+      const float k = (dm1 * A - B) + 12582912.0f;
+      n = 1 + (__float_as_int(k) - 0x4b400000);
+    } else if (d == 0 && solid_at(x, y, z)) {
+      return true;
+    }
+    if (n >= rem) return false;  // the march runs out inside space known to be empty: a miss
+    rem -= n;
+    RM_STAT_SKIP(n);
+    for (; n >= 8; n -= 8) {
+      p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+      p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+    }
+    if (n & 4) { p = p + delta; p = p + delta; p = p + delta; p = p + delta; }
+    if (n & 2) { p = p + delta; p = p + delta; }
+    if (n & 1) p = p + delta;
+  }
+  return false;
+}
+
+// renderer.cl:209-237 without the normal; g = rpos.y + groundY is passed in by the caller (it has it).
+// Shared by the sphere traces and the AO probes: one copy of the march loop in the kernel.
+#ifndef RM_FUSED_SD_ATTR
+#define RM_FUSED_SD_ATTR __device__ __noinline__
+#endif
+template <bool kCount, bool kNib>
+RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 delta, int steps, float invS, float g,
+                                    bool smooth) {
+  const RmOpts& o = g_opts;
+  Hit r;
+  r.dist = g < 1e5f ? g : 1e5f;
+  r.hit = false;
+  r.closer = false;
+  r.p = f3s(0.0f);
+  const bool inside = rpos.x > o.boundsMin.x && rpos.x < o.boundsMax.x && rpos.y > o.boundsMin.y &&
+                      rpos.y < o.boundsMax.y && rpos.z > o.boundsMin.z && rpos.z < o.boundsMax.z;
+  const bool away = (rpos.x > o.boundsMax.x && dir.x > 0.0f) || (rpos.x < o.boundsMin.x && dir.x < 0.0f) ||
+                    (rpos.y > o.boundsMax.y && dir.y > 0.0f) || (rpos.y < o.boundsMin.y && dir.y < 0.0f) ||
+                    (rpos.z > o.boundsMax.z && dir.z > 0.0f) || (rpos.z < o.boundsMin.z && dir.z < 0.0f);
+  const float idist = inside ? 0.0f : (away ? -1.0f : box_entry(o.boundsMin, o.boundsMax, rpos, dir));
+  RM_STAT_EVENT(0);
+  RM_STAT_EVENT(inside ? 1 : (away ? 2 : 3));
+  if (idist >= 0.0f && idist < r.dist) {
+    RM_STAT_EVENT(4);
+    float3 p = rpos + o.voxelBounds;
+    if (idist > 0.0f) p = dir * idist + p;
+    p = p * o.invVoxelScale;
+    bool found;
+    if constexpr (kCount) found = march_counting<kNib>(c, p, delta, steps, invS);
+    else found = march_fast<kNib>(p, delta, steps, invS);
+    if (found) {
+      RM_STAT_EVENT(5);
+      r.hit = true;
+      r.p = p;
+      if constexpr (kCount) {
+        const int x = f2i_sat(p.x * (float)o.rx), y = f2i_sat(p.y * (float)o.ry), z = f2i_sat(p.z * (float)o.rz);
+        c.taps += taps_of_hit(x, y, z, smooth);
+      }
+      const float3 hp = p * o.voxelBounds2 + (-o.voxelBounds);
+      const float d = len3(rpos - hp) - o.voxelSize;
+      if (d < r.dist) { r.dist = d; r.closer = true; }
+    }
+  }
+  return r;
+}
+
+// per-direction constants of the march: delta (renderer.cl:215) and 1 / (largest step in voxels)
+RM_DEV float3 march_delta(float3 dir, int steps, float& invS) {
+  const RmOpts& o = g_opts;
+  const float3 delta = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
+  const float sm = fmaxf(fmaxf(fabsf(delta.x) * (float)o.rx, fabsf(delta.y) * (float)o.ry), fabsf(delta.z) * (float)o.rz);
+  invS = sm > 5e-4f ? __fdividef(1.0f, sm) : 2000.0f;
+  return delta;
+}
+
+// The march window of a trace (see rm_scene_plain.cuh:march_window for the argument).
+RM_DEV void march_window(float3 ro, float3 rd, float maxDist, float& tin, float& tout) {
+  const RmOpts& o = g_opts;
+  const float kGrow = 0.01f, kTiny = 1e-5f, kBig = 64.0f, kInf = 3.0e38f;
+  tin = -kInf;
+  tout = kInf;
+  const float ro_[3] = {ro.x, ro.y, ro.z}, rd_[3] = {rd.x, rd.y, rd.z};
+  const float lo_[3] = {o.boundsMin.x, o.boundsMin.y, o.boundsMin.z}, hi_[3] = {o.boundsMax.x, o.boundsMax.y, o.boundsMax.z};
+  bool ok = maxDist <= kBig, miss = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    ok = ok && fabsf(ro_[i]) <= kBig && fabsf(lo_[i]) <= kBig && fabsf(hi_[i]) <= kBig && fabsf(rd_[i]) <= 2.0f;
+  if (!ok) return;
+  float a = -kInf, b = kInf;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float l = lo_[i] - kGrow - ro_[i], h = hi_[i] + kGrow - ro_[i];
+    if (fabsf(rd_[i]) < kTiny) {
+      if (l > 0.0f || h < 0.0f) miss = true;
+    } else {
+      const float inv = __fdividef(1.0f, rd_[i]);
+      const float t0 = l * inv, t1 = h * inv;
+      a = fmaxf(a, fminf(t0, t1));
+      b = fminf(b, fmaxf(t0, t1));
+    }
+  }
+  if (miss || b < a) { tin = kInf; tout = -kInf; return; }
+  tin = a;
+  tout = b;
+}
+
+// renderer.cl:239-257. One copy for the primary / bounce / shadow traces.
+#ifndef RM_FUSED_ST_ATTR
+#define RM_FUSED_ST_ATTR __device__ __noinline__
+#endif
+template <bool kCount, bool kNib>
+RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist, int maxSteps, bool smooth,
+                                   bool wantSurface) {
+  const RmOpts& o = g_opts;
+  RM_STAT_TRACE();
+  RM_STAT_EVENT(wantSurface ? 6 : 7);
+  float invS;
+  const float3 delta = march_delta(rd, o.maxVoxelIter, invS);
+  Hit j;
+  j.dist = 0.0f; j.hit = false; j.closer = false; j.p = f3s(0.0f);
+  float jg = 0.0f;  // ground distance of the last evaluation (the ground's "id" is (int)g, renderer.cl:211)
+  float dist = o.startDist;
+  float3 pos = ro;
+  const float inv_step = kCount ? 0.0f : 1.01f / len3(delta * o.voxelBounds2);
+  bool cut = false;
+  float tin = -3.0e38f, tout = 3.0e38f;
+  if (!kCount) march_window(ro, rd, maxDist, tin, tout);
+  while (--maxSteps >= 0) {
+    if constexpr (kCount) c.outer++;
+    RM_STAT_EVENT(wantSurface ? 8 : 9);
+    pos = ro + rd * dist;
+    const float g = pos.y + o.groundY;
+    jg = g;
+    if (!kCount && (dist > tout || tin - dist > g * 1.0001f + 1e-3f || g <= 0.0f)) {
+      RM_STAT_EVENT(12);
+      j.dist = g < 1e5f ? g : 1e5f;
+      j.hit = false;
+      j.closer = false;
+      cut = false;
+      if (dist > tout && rd.y >= 0.0f && g > o.eps && g < 1e5f && maxSteps < 65536 &&
+          (float)(maxSteps + 1) * g * 0.99f >= maxDist - dist) {
+        RM_STAT_EVENT(17);
+        dist = maxDist;
+        break;
+      }
+    } else {
+      int limit = o.maxVoxelIter;
+      if (!kCount) {
+        float reach = g;
+        if (!wantSurface) reach = fminf(reach, fmaxf(maxDist - dist, o.eps));
+        const float k = (reach + o.voxelSize) * inv_step;
+        cut = k < (float)(limit - 2);
+        if (cut) limit = f2i_sat(k) + 2;
+      }
+      j = scene_distance<kCount, kNib>(c, pos, rd, delta, limit, invS, g, smooth);
+    }
+    if (fabsf(j.dist) <= o.eps || dist >= maxDist) break;
+    dist += j.dist;
+  }
+  if (!kCount && wantSurface && cut && !j.hit) {
+    RM_STAT_EVENT(10);
+    j = scene_distance<kCount, kNib>(c, pos, rd, delta, o.maxVoxelIter, invS, jg, smooth);
+  }
+  const bool miss = dist >= maxDist;
+  if (miss) {
+    pos = ro + rd * dist;
+    dist = 1000.0f;
+  }
+  Isec r;
+  r.distance = dist;
+  r.pos = pos;
+  r.objectID = -1;
+  r.normal = f3s(0.0f);
+  if (!wantSurface) return r;  // shadow rays use the distance only
+  const int x = f2i_sat(j.p.x * (float)o.rx), y = f2i_sat(j.p.y * (float)o.ry), z = f2i_sat(j.p.z * (float)o.rz);
+  if (!miss) {
+    if (j.closer) {
+      const int v = voxel_value(x, y, z);
+      r.objectID = v < 168 ? (v < 84 ? 1 : 2) : 3;  // voxelMaterial, renderer.cl:205-207
+    } else {
+      r.objectID = f2i_sat(jg < 1e5f ? jg : -1.0f);
+    }
+  }
+  if (j.hit) r.normal = smooth ? normal_smooth(x, y, z) : normal_6tap(x, y, z);
+  else r.normal = jg < 1e5f ? f3(0.0f, 1.0f, 0.0f) : -rd;
+  return r;
+}
+
+RM_DEV float3 sky(float3 d) { return lerp3(g_opts.sky1, g_opts.sky2, d.y * 0.5f + 0.5f); }  // :259-261
+
+// renderer.cl:263-269
+RM_SHARED_FN float3 light_pos(Lane s, float px, float py, int i) {
+  const uint32_t seed = f2u_wrap(px * 1957.0f + py * 2173.0f + s.time * 4763.742f);
+  return table_xyz(s, seed) * g_opts.lightScatter + g_opts.lightPos[i];
+}
+
+RM_DEV float3 reflect3(float3 v, float3 n) { return v - n * (2.0f * dot3(v, n)); }  // :271-273
+
+// renderer.cl:275-290
+RM_SHARED_FN float3 atmosphere(Lane s, float px, float py, float3 ro, float3 rd, float distance, float3 col) {
+  const RmOpts& o = g_opts;
+  const float fa = 1.0f - expf(distance * distance * -o.fogPow);
+  col = (sky(rd) - col) * fa + col;
+  for (int i = 0; i < o.numLights; ++i) {
+    float3 lp = light_pos(s, px, py, i);
+    const float d = cl_clamp(dot3(lp - ro, rd), 0.0f, distance);
+    lp = rd * d + (ro - lp);
+    col = o.lightColor[i] * (o.flareAmp / dot3(lp, lp)) + col;
+  }
+  return col;
+}
+
+// renderer.cl:304-311
+RM_DEV float schlick(float r0, float smooth, float3 n, float3 view) {
+  const float d = cl_clamp(1.0f - dot3(n, -view), 0.0f, 1.0f);
+  if (d > 0.0f) {
+    const float d2 = d * d;
+    return (1.0f - r0) * (smooth * d2 * d2 * d) + r0;
+  }
+  return 0.0f;
+}
+
+// renderer.cl:317-325
+RM_DEV float blinn_phong(float smooth, float3 rd, float3 ldir, float3 n) {
+  const float nh = dot3(unit3(ldir - rd), n);
+  if (nh > 0.0f) {
+    const float sp = exp2f(6.0f * smooth + 4.0f);
+    return powf(nh, sp) * (sp + 2.0f) * 0.125f;
+  }
+  return 0.0f;
+}
+
+// renderer.cl:327-346
+template <bool kCount, bool kNib>
+RM_DEV float ambient_occlusion(RM_CNT c, Lane s, float3 pos, float3 n0) {
+  const RmOpts& o = g_opts;
+  float ao = 1.0f, d = 0.0f;
+  uint32_t seed = f2u_wrap(pos.x * 3183.75f + pos.y * 1831.42f + pos.z * 2945.87f + s.time * 2671.918f);
+  for (int i = 0; i <= o.aoIter && ao > 0.01f; ++i) {
+    d += o.aoStepDist;
+    seed += 37u;
+    const float3 n = unit3(table_xyz(s, seed) * 0.2f + n0);
+    const float3 q = n * d + pos;
+    const float g = q.y + o.groundY;
+    float hdist;
+    const float out = fmaxf(fmaxf(fmaxf(o.boundsMin.x - q.x, q.x - o.boundsMax.x), fmaxf(o.boundsMin.y - q.y, q.y - o.boundsMax.y)),
+                            fmaxf(o.boundsMin.z - q.z, q.z - o.boundsMax.z));
+    if (!kCount && o.aoAmp >= 0.0f && d > 0.0f && out > d + o.voxelSize + 1e-3f && out < 1e3f) {
+      RM_STAT_EVENT(18);
+      hdist = g < 1e5f ? g : 1e5f;
+    } else {
+      float invS;
+      const int msteps = o.maxVoxelIter / 2;
+      const float3 delta = march_delta(n, msteps, invS);
+      int limit = msteps;
+      if (!kCount && o.aoAmp >= 0.0f && d > 0.0f) {
+        const float k = (d + o.voxelSize) * 1.01f / len3(delta * o.voxelBounds2);
+        if (k < (float)msteps) limit = f2i_sat(k) + 2 < msteps ? f2i_sat(k) + 2 : msteps;
+      }
+      RM_STAT_EVENT(11);
+      RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16 + 8 + i);
+      hdist = scene_distance<kCount, kNib>(c, q, n, delta, limit, invS, g, false).dist;
+    }
+    ao *= 1.0f - cl_max((d - hdist) * o.aoAmp / d, 0.0f);
+  }
+  return ao;
+}
+
+// renderer.cl:348-381 (shadow :292-301 inlined). One copy for the primary and the bounce surfaces.
+#ifndef RM_FUSED_OL_ATTR
+#define RM_FUSED_OL_ATTR __device__ __noinline__
+#endif
+template <bool kCount, bool kNib>
+RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float px, float py, float3 rd, float3 ipos, int mat, float3 n,
+                                        float3 reflectCol) {
+  const RmOpts& o = g_opts;
+  const RmMaterial& m = o.mat[mat];
+  const float ao = ambient_occlusion<kCount, kNib>(c, s, ipos, n);
+  float3 diff = sky(n) * ao;
+  float3 spec = reflectCol * ao;
+  float3 fin = f3s(0.0f);
+  for (int i = 0; i < o.numLights; ++i) {
+    const float3 dl = light_pos(s, px, py, i) - ipos;
+    const float ld2 = dot3(dl, dl);
+    const float att = 1.0f / ld2;
+    if (att > o.minLightAtt) {
+      const float3 ldir = unit3(dl);
+      const float lmax = cl_min(sqrtf(ld2) - o.shadowBias, o.maxDist);
+      const float kd = cl_max(0.0f, dot3(ldir, n));
+      const float ks = blinn_phong(m.smoothness, rd, ldir, n);
+      const float3 inc = (o.lightColor[i] * 1.0f) * att;  // (lightColor * shadow factor 1) * att, :369
+      const float3 zero = inc * 0.0f;
+      const bool irrelevant = !kCount && kd == 0.0f && ks == 0.0f && zero.x == 0.0f && zero.y == 0.0f && zero.z == 0.0f;
+      if (!irrelevant) {
+        RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16 + 1 + i);
+        const Isec sh = sphere_trace<kCount, kNib>(c, ipos + ldir * o.shadowBias, ldir, lmax, o.shadowIter, false, false);
+        const float sf = sh.distance < lmax ? 0.0f : 1.0f;
+        if (sf > 0.0f) {
+          diff = diff + inc * kd;
+          spec = spec + inc * ks;
+        }
+      }
+    }
+    diff = diff * m.albedo;
+    fin = fin + lerp3(diff, spec, schlick(m.r0, m.smoothness, n, rd));
+  }
+  return fin / (float)o.numLights;
+}
+
+RM_DEV int mat_index(int id) { return id < 0 ? 0 : (id > 3 ? 3 : id); }
+
+// renderer.cl:407-446 with basicSceneColor (:383-405) in its bounce loop
+template <bool kCount, bool kNib>
+RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal, float3 ro, float3 rd) {
+  const RmOpts& o = g_opts;
+  RM_STAT_LEVEL(0);
+  RM_STAT_SITE(0);
+  const Isec isec = sphere_trace<kCount, kNib>(c, ro, rd, o.maxDist, o.maxIter, true, true);
+  float3 col;
+  if (isec.distance >= o.maxDist) {
+    col = sky(rd);
+  } else {
+    const int mi = mat_index(isec.objectID);
+    const RmMaterial& m = o.mat[mi];
+    const float3 n = mcNormal * (1.0f / (m.smoothness * 200.0f + 5.0f)) + isec.normal;
+    float3 reflectCol = f3s(0.0f);
+    if (m.r0 > 0.0f && o.reflectIter > 0) {
+      float3 bpos = isec.pos, bn = n, bd = rd;
+      for (int i = 0; i < o.reflectIter; ++i) {
+        bd = reflect3(bd, bn);
+        const float3 bo = bpos + bd * 0.0075f;
+        RM_STAT_LEVEL(i + 1);
+        RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16);
+        const Isec ri = sphere_trace<kCount, kNib>(c, bo, bd, o.maxDist, o.maxIter, false, true);
+        float3 bc;
+        if (ri.objectID < 0) bc = sky(bd);
+        else bc = object_lighting<kCount, kNib>(c, s, px, py, bd, ri.pos, mat_index(ri.objectID), ri.normal,
+                                                sky(reflect3(bd, ri.normal)));
+        reflectCol = reflectCol + atmosphere(s, px, py, bo, bd, ri.distance, bc);
+        if (ri.objectID < 0) break;
+        if (o.mat[mat_index(ri.objectID)].r0 < 0.001f) break;
+        bpos = ri.pos;
+        bn = ri.normal;
+      }
+    } else {
+      reflectCol = sky(reflect3(rd, n));
+    }
+    RM_STAT_LEVEL(0);
+    col = object_lighting<kCount, kNib>(c, s, px, py, rd, isec.pos, mi, n, reflectCol);
+  }
+  return atmosphere(s, px, py, ro, rd, isec.distance, col);
+}
+
+// One work-item of RenderImage (renderer.cl:478-494; initRenderState :467-476, cameraRayLookat
+// :456-465): returns sceneColor * exposure.
+template <bool kCount, bool kNib>
+RM_DEV float3 render_pixel_sample(RM_CNT c, Lane s, int id) {
+  const RmOpts& o = g_opts;
+  const float4 a = table_at(s, (uint32_t)(id * 17) + f2u_wrap(s.time * 3141.3862f));
+  const float3 mcNormal = unit3(table_xyz(s, (uint32_t)(id * 37) + f2u_wrap(s.time * 1859.1467f)));
+  const float px = (float)(id % o.width) + a.z;
+  const float py = (float)(id / o.width) + a.w;
+  const float3 eye = f3(mcNormal.z, mcNormal.x, mcNormal.y) * o.dof + o.eyePos;
+  const float3 fwd = unit3(o.targetPos - eye);
+  const float3 right = unit3(cross3(fwd, o.up));
+  const float vx = px / (float)o.width * o.fov - o.fov * 0.5f;
+  float vy = py / (float)o.height * o.fov - o.fov * 0.5f;
+  vy = vy * -o.invAspect;
+  const float3 rd = unit3(right * vx + cross3(right, fwd) * vy + fwd);
+  return scene_color<kCount, kNib>(c, s, px, py, mcNormal, eye, rd) * o.exposure;
+}
+
+}  // namespace fused

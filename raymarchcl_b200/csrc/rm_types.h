@@ -57,6 +57,9 @@ struct RmAccel {
   int cell_shift;             // macro-cell edge = 1 << cell_shift voxels (>= 2)
   float cellf;                // (float)(1 << cell_shift)
   float rxf, ryf, rzf;        // (float) of the grid extents: the march multiplies by them at every lookup
+  const uint8_t* nib;         // the same map packed to 4 bits per cell (min(dist, 15)); cell c = nibble c&1 of byte c>>1.
+                              // The default kernel stages it into shared memory with a bulk TMA copy
+  unsigned nib_bytes;         // its size, padded to a multiple of 16 bytes (bulk-copy granularity)
 };
 
 struct RmAccelStorage {  // owner of the device arrays behind an RmAccel view
@@ -65,6 +68,7 @@ struct RmAccelStorage {  // owner of the device arrays behind an RmAccel view
   uint64_t* d_occ = nullptr;
   uint8_t* d_dist = nullptr;
   uint8_t* d_tmp = nullptr;
+  uint8_t* d_nib = nullptr;
   unsigned* d_flag = nullptr;
   size_t brick_capacity = 0, cell_capacity = 0;
   int iso = -1;

@@ -153,6 +153,43 @@ class Renderer:
         n, oarr, marr, keep = self._ptr_arrays(opts, mcs)
         self._check(self._lib.rm_upload_passes(self._h, oarr, marr, n))
 
+    def update_opts(self, opts: Sequence[bytes]) -> None:
+        """``update-render-option-buffer`` (core.clj:108-117) for resident passes: new opts, same tables."""
+        n = len(opts)
+        obufs = [C.create_string_buffer(o, OPTS_BYTES) for o in opts]
+        oarr = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in obufs])
+        self._check(self._lib.rm_update_opts(self._h, oarr, n))
+
+    def set_volume_device(self, dptr: int, rx: int, ry: int, rz: int) -> None:
+        """Volume already in device memory (``uint8[rz][ry][rx]``): one device-to-device copy."""
+        self._check(self._lib.rm_set_volume_device(self._h, C.c_void_p(dptr), int(rx), int(ry), int(rz)))
+        self.vres = (int(rx), int(ry), int(rz))
+
+    def tonemap_async(self, opts: bytes, out: np.ndarray, slot: int) -> None:
+        """Queue TonemapImage + the read-back into ``out`` (pinned uint32[H*W]); :meth:`wait` completes it."""
+        if out.dtype != np.uint32 or out.size != self.width * self.height or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous uint32 array of width*height words")
+        self._check(self._lib.rm_tonemap_async(self._h, C.c_char_p(opts), len(opts), out.ctypes.data, int(slot)))
+
+    def wait(self, slot: int) -> None:
+        self._check(self._lib.rm_wait(self._h, int(slot)))
+
+    def alloc_pinned_argb(self) -> np.ndarray:
+        """A page-locked uint32[width*height] host buffer (``rm_host_alloc``) for :meth:`tonemap_async`."""
+        n = self.width * self.height
+        p = C.c_void_p()
+        self._check(self._lib.rm_host_alloc(self._h, n * 4, C.byref(p)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,))
+
+    def free_pinned(self, buffers) -> None:
+        for b in buffers:
+            if b is not None and self._h:
+                self._lib.rm_host_free(self._h, C.c_void_p(b.ctypes.data))
+
+    def set_argb_target(self, dptr: Optional[int], packed: bool = False) -> None:
+        """Device buffer the default kernel fills with ARGB words while it renders (None: own frame)."""
+        self._check(self._lib.rm_set_argb_target(self._h, C.c_void_p(dptr or 0), int(packed)))
+
     def render_resident(self, first: int, count: int) -> None:
         self._check(self._lib.rm_render_resident(self._h, int(first), int(count)))
 
@@ -319,26 +356,48 @@ def test_render(width: int = 640, height: int = 360, iter: int = 1, vres: int = 
 def test_anim(width: int, height: int, iter: int, res: int, mat: str, vname: Optional[str] = None,
               frames: int = 35, out_dir: Optional[str] = None, device: int = 0, volume=None) -> List[np.ndarray]:
     """``test-anim`` (core.clj:181-213): one ``init-renderer``, then per frame an orbiting camera
-    (theta 0..350 deg over ``frames`` frames, r 2.25, eye y 0.44..0.45, target y -0.15, fov 115),
-    ``update-render-option-buffer`` and a pipeline run. The volume is uploaded once and stays
-    resident (the reference's step list re-uploads it every frame, core.clj:81). Returns the ARGB
-    frames; writes ``frame-%04d.png`` into ``out_dir`` when given."""
+    (theta 0..350 deg over ``frames`` frames, r 2.25, eye y 0.44..0.45, target y -0.15, fov 115) and
+    ``update-render-option-buffer``. The reference's step list re-uploads the volume and every table
+    on every frame (core.clj:81,84); here they are uploaded ONCE (``rm_set_volume``,
+    ``rm_upload_passes``), a frame costs ``iter`` x 544 bytes of opts (``rm_update_opts``), and the
+    ARGB read-back of frame k (``rm_tonemap_async`` into one of two pinned host buffers) overlaps the
+    render of frame k+1. Returns the ARGB frames; writes ``frame-%04d.png`` into ``out_dir`` when given."""
     args = {"width": width, "height": height, "vres": [res, res, res], "iter": iter, "mat": mat,
             "vname": vname, "volume": volume}
     state = init_renderer(args, device=device)
+    r: Renderer = state["cl-state"]
     out: List[np.ndarray] = []
+
+    def collect(frame: int, slot: int) -> None:
+        r.wait(slot)
+        argb = host[slot].reshape(height, width).copy()
+        out.append(argb)
+        if out_dir:
+            from PIL import Image
+            rgb = np.stack([(argb >> 16) & 255, (argb >> 8) & 255, argb & 255], axis=-1).astype(np.uint8)
+            Image.fromarray(rgb, "RGB").save(os.path.join(out_dir, "frame-%04d.png" % frame))
+
+    host = []
     try:
+        r.set_volume(state["v-buf"])
+        r.clear_accum(width, height)
+        host = [r.alloc_pinned_argb() for _ in range(2)]
+        r.upload_passes(state["opts-buffers"], state["mc-buffers"])
         for frame in range(frames):
+            slot = frame & 1
+            if frame >= 2:
+                collect(frame - 2, slot)
             t = frame / float(frames)                       # m/map-interval frame 0 35 0.0 1.0
             frame_args = {"fov": 115.0, "targetpos": [0, -0.15, 0],
                           "eyepos": compute_eyepos(350.0 * t, 2.25, 0.44 + 0.01 * t)}
             update_render_option_buffer(state, frame_args)
-            argb = execute_pipeline(state, make_pipeline(state))
-            out.append(argb)
-            if out_dir:
-                from PIL import Image
-                rgb = np.stack([(argb >> 16) & 255, (argb >> 8) & 255, argb & 255], axis=-1).astype(np.uint8)
-                Image.fromarray(rgb, "RGB").save(os.path.join(out_dir, "frame-%04d.png" % frame))
+            r.update_opts(state["opts-buffers"])
+            r.clear_accum(width, height)
+            r.render_resident(0, len(state["opts-buffers"]))
+            r.tonemap_async(state["opts-buffers"][0], host[slot], slot)
+        for frame in range(max(0, frames - 2), frames):
+            collect(frame, frame & 1)
     finally:
-        state["cl-state"].close()
+        r.free_pinned(host)
+        r.close()
     return out

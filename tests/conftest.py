@@ -35,7 +35,19 @@ def ref_strict():
 
 @pytest.fixture(scope="session")
 def gpu_renderer():
+    from raymarchcl_b200 import _lib
     from raymarchcl_b200.renderer import Renderer
-    r = Renderer(0)
+    try:
+        lib = _lib.load()
+    except (ImportError, OSError) as e:
+        pytest.skip(f"libraymarch_b200.so not loadable: {e}")
+    if lib.rm_device_count() == 0:
+        pytest.skip("no CUDA device (run the gpu-marked tests on the B200 box)")
+    try:
+        r = Renderer(0)
+    except _lib.RaymarchError as e:
+        if e.code == -6:  # RM_ERR_NO_DEVICE: not an sm_100 device
+            pytest.skip(str(e))
+        raise
     yield r
     r.close()

@@ -42,6 +42,7 @@ static inline int stat_bucket(int n) {
 }
 
 #include "rm_scene_plain.cuh"
+#include "rm_scene_fused.cuh"
 #include "rm_wave.cuh"
 
 namespace {
@@ -82,7 +83,7 @@ void decode_opts(const void* blob, RmOpts* o) {
 // CPU restatement of rm_accel.cu
 struct HostAccel {
   std::vector<uint64_t> solid, occ;
-  std::vector<uint8_t> dist;
+  std::vector<uint8_t> dist, nib;  // nib: rm_accel.cu:k_pack_nibbles restated
   RmAccel view{};
 };
 
@@ -141,6 +142,10 @@ void build_accel(const uint8_t* vox, int rx, int ry, int rz, int iso, int cell_s
   a.solid = A.solid.data();
   a.occ = A.occ.data();
   a.dist = A.dist.data();
+  A.nib.assign(((nc + 1) / 2 + 15) & ~(size_t)15, 0);
+  for (size_t c = 0; c < nc; ++c) A.nib[c >> 1] |= (uint8_t)(std::min<int>(A.dist[c], 15) << ((c & 1) * 4));
+  a.nib = A.nib.data();
+  a.nib_bytes = (unsigned)A.nib.size();
 }
 
 float* g_cost_out = nullptr;  // optional: count x 64 floats, per-site cost of every rendered pixel-sample
@@ -171,8 +176,11 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
       std::memcpy(g_accel_key, key, sizeof key);
     }
     plain::g_accel = g_host_accel.view;
+    fused::g_accel = g_host_accel.view;
+    fused::rm_host_nib = g_host_accel.nib.data();
   }
   plain::g_opts = o;
+  fused::g_opts = o;
   const int count = ids ? nids : n;
   unsigned long long cs = 0, ct = 0, co = 0;
 #pragma omp parallel reduction(+ : cs, ct, co)
@@ -185,9 +193,18 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
       std::memset(t_site_cost, 0, sizeof t_site_cost);
       t_site = 0; t_level = 0; t_eval_n = 0;
       float3 c;
+      // modes 3..6: the default kernel's routine (rm_scene_fused.cuh): production / counting over the
+      // 4-bit map (what the kernel reads from shared memory), production / counting over the byte map
+      const fused::Lane lane{reinterpret_cast<const float4*>(mc), o.time};
+      fused::Cnt<true> fc;
       if (mode == 0) c = plain::render_pixel_sample<false>(s, plain::BrickVolume{}, id);
       else if (mode == 1) c = plain::render_pixel_sample<true>(s, plain::BrickVolume{}, id);
-      else c = plain::render_pixel_sample<true>(s, plain::ByteVolume{vox}, id);
+      else if (mode == 2) c = plain::render_pixel_sample<true>(s, plain::ByteVolume{vox}, id);
+      else if (mode == 3) c = fused::render_pixel_sample<false, true>(fused::Cnt<false>{}, lane, id);
+      else if (mode == 4) c = fused::render_pixel_sample<true, true>(fc, lane, id);
+      else if (mode == 5) c = fused::render_pixel_sample<false, false>(fused::Cnt<false>{}, lane, id);
+      else c = fused::render_pixel_sample<true, false>(fc, lane, id);
+      if (mode == 4 || mode == 6) { s.w.steps = fc.steps; s.w.taps = fc.taps; s.w.outer = fc.outer; }
       float* px = pixels + 4 * (size_t)id;
       const float3 m = lerp3(make_float3(px[0], px[1], px[2]), c, o.frameBlend);  // mix(), renderer.cl:492
       px[0] = m.x; px[1] = m.y; px[2] = m.z; px[3] = 1.0f;

@@ -13,7 +13,8 @@ _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 
 STAT_NAMES = ["lookups", "skips", "skipped_samples", "jumps", "jump_samples", "seq_adds", "marches", "traces"]
-MODES = {"production": 0, "counting": 1, "bytes": 2, "wave": 0, "wave_counting": 1}
+MODES = {"production": 0, "counting": 1, "bytes": 2, "wave": 0, "wave_counting": 1,
+         "fused": 3, "fused_counting": 4, "fused_bytemap": 5, "fused_bytemap_counting": 6}
 
 
 class HostSim:

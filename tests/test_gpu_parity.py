@@ -54,7 +54,7 @@ def render_gpu(r, vol, opts, mcs, w, h, fused=True, count=True):
     return r.read_accum(), r.tonemap(opts[0]), np.array([st["steps"], st["taps"], st["outer_iters"]], np.uint64)
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 3], ids=["fast", "plain", "wave"])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 4], ids=["fast", "plain", "wave", "bricks"])
 @pytest.mark.parametrize("name", sorted(GOLDEN_SCENES))
 def test_gpu_matches_reference_golden(gpu_renderer, name, kernel):
     gold = np.load(os.path.join(GOLD, "frames.npz"))
@@ -78,7 +78,7 @@ SCENES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 3], ids=["fast", "plain", "wave"])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 4], ids=["fast", "plain", "wave", "bricks"])
 @pytest.mark.parametrize("kw", SCENES, ids=lambda k: f"{k.get('volume', 'gyroid')}{k['vres']}_{k['mat']}_{k['width']}x{k['height']}")
 def test_gpu_matches_oracle(gpu_renderer, oracle, kw, kernel):
     vol, opts, mcs = build_scene(**kw)

@@ -116,7 +116,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.rm_abi_version.restype = ctypes.c_int
-    assert lib.rm_abi_version() == 1
+    assert lib.rm_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

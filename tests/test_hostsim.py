@@ -37,7 +37,11 @@ def orc():
 
 @pytest.mark.parametrize("name", list(GOLDEN_SCENES) + list(EXTRA_SCENES))
 @pytest.mark.parametrize("mode,cell_shift", [("production", 2), ("production", 3), ("counting", 2), ("bytes", 2),
-                                             ("wave", 2), ("wave_counting", 2)])  # wave*: the wavefront stages of rm_wave.cuh
+                                             ("wave", 2), ("wave_counting", 2),  # wave*: the wavefront stages of rm_wave.cuh
+                                             # fused*: the default kernel's routine (rm_scene_fused.cuh) over the 4-bit
+                                             # distance map it reads from shared memory / over the byte map
+                                             ("fused", 2), ("fused", 3), ("fused_counting", 2), ("fused_bytemap", 2),
+                                             ("fused_bytemap_counting", 3)])
 def test_host_build_of_the_kernel_routine_is_bit_identical_to_the_oracle(sim, orc, name, mode, cell_shift):
     kw = GOLDEN_SCENES.get(name) or EXTRA_SCENES[name]
     vol, opts, mcs = build_scene(**kw)
@@ -46,7 +50,7 @@ def test_host_build_of_the_kernel_routine_is_bit_identical_to_the_oracle(sim, or
     px, cnt = sim.render_frame(vol, mcs, opts, w, h, mode=mode, cell_shift=cell_shift)
     assert np.array_equal(px.view(np.uint32), ref.view(np.uint32)), (
         f"{name}/{mode}: {(px.view(np.uint32) != ref.view(np.uint32)).any(axis=-1).sum()} pixels differ")
-    if mode not in ("production", "wave"):
+    if mode not in ("production", "wave", "fused", "fused_bytemap"):
         assert np.array_equal(cnt, ref_cnt)
 
 
@@ -62,7 +66,7 @@ def test_production_march_elides_most_fetches(sim):
 
 
 @pytest.mark.parametrize("vres", [(96, 40, 130), (33, 70, 45)], ids=str)
-@pytest.mark.parametrize("mode", ["production", "counting", "wave"])
+@pytest.mark.parametrize("mode", ["production", "counting", "wave", "fused", "fused_counting"])
 def test_ragged_grids(sim, orc, vres, mode):
     """Extents that are neither equal nor multiples of the brick / macro-cell edge."""
     from raymarchcl_b200 import compute_eyepos, generate_scatter_offsets, make_gyroid_volume, make_render_option_buffers
@@ -74,5 +78,5 @@ def test_ragged_grids(sim, orc, vres, mode):
     ref, ref_cnt = orc.render_frame(vol, mcs, opts, w, h)
     px, cnt = sim.render_frame(vol, mcs, opts, w, h, mode=mode, cell_shift=3 if mode == "wave" else 2)
     assert np.array_equal(px.view(np.uint32), ref.view(np.uint32))
-    if mode == "counting":
+    if mode in ("counting", "fused_counting"):
         assert np.array_equal(cnt, ref_cnt)

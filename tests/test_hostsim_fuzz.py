@@ -83,12 +83,13 @@ def test_random_options_production_routine_is_bit_identical(checkers, seed):
     assert decode_render_opts(opts[0])["numLights"] == fields["numLights"]
     mcs = [generate_scatter_offsets(0x4000, 77 + seed + i) for i in range(2)]
     ref, ref_cnt = orc.render_frame(vol, mcs, opts, W, H)
-    for mode, shift in (("production", 2), ("production", 3), ("counting", 2), ("wave", 2), ("wave_counting", 2)):
+    for mode, shift in (("production", 2), ("production", 3), ("counting", 2), ("wave", 2), ("wave_counting", 2),
+                        ("fused", 2), ("fused", 3), ("fused_counting", 2), ("fused_bytemap", 2)):
         px, cnt = sim.render_frame(vol, mcs, opts, W, H, mode=mode, cell_shift=shift)
         same = px.view(np.uint32) == ref.view(np.uint32)
         both_nan = np.isnan(px) & np.isnan(ref)  # NaN payloads may differ; NaN-ness may not
         assert (same | both_nan).all(), f"seed {seed} {mode}: {(~(same | both_nan)).any(axis=-1).sum()} pixels differ; {fields}"
-        if mode in ("counting", "wave_counting"):
+        if mode in ("counting", "wave_counting", "fused_counting"):
             assert np.array_equal(cnt, ref_cnt)
 
 

@@ -67,7 +67,7 @@ def test_non_finite_points_are_rejected(orc):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CLOUDS))
 @pytest.mark.parametrize("res,ks", [(32, -1), (48, 1), (96, 3)])
-def test_cuda_voxeliser_equals_the_restatement(orc, name, res, ks):
+def test_cuda_voxeliser_equals_the_restatement(gpu_renderer, orc, name, res, ks):
     from raymarchcl_b200.renderer import Renderer
     pts = CLOUDS[name]
     ref = orc.voxelize_points(pts, res, ks)
@@ -78,7 +78,7 @@ def test_cuda_voxeliser_equals_the_restatement(orc, name, res, ks):
 
 
 @pytest.mark.gpu
-def test_cuda_voxeliser_large_cloud_and_render(orc):
+def test_cuda_voxeliser_large_cloud_and_render(gpu_renderer, orc):
     """A 2M-vertex cloud at 256^3, then rendered straight from the device-resident result."""
     from raymarchcl_b200.renderer import Renderer
     from tests.scenes import build_scene
