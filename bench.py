@@ -400,6 +400,7 @@ def run_b200(args):
                 parity["checker"] = "oracle/rm_oracle.c (strict fp32 restatement, pinned to the reference text)"
             barrier()
 
+
         # ---- end to end through the host-buffer calls ----
         e2e = None
         if not args.no_e2e:
@@ -471,214 +472,6 @@ def run_b200(args):
             "note": "1 B per reference-equivalent voxel fetch (inner steps + occupancy taps). The volume and its "
                     "derived tables are L1/L2/shared-memory resident and most fetches are elided, so DRAM traffic stays "
                     "far below the algorithmic bytes by design; the kernel is instruction-issue bound (DESIGN.md 4-5)"}
-
-    line = {
-        "impl": "reference", "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "frames_per_s": value * 1e6 / (steps_sample * stride) if steps_sample else None,
-        "frames_per_s_note": "extrapolated from the sample by the step ratio",
-        "config": {"workload": wl["name"], "reference_build": name, "host": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    _emit(line)
-
-
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from raymarchcl_b200 import _lib
-    from raymarchcl_b200.dist import FrameGatherer, ShardLayout
-    from raymarchcl_b200.renderer import Renderer
-    from tests.scenes import build_scene
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the render op has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    wl = WORKLOADS[args.workload]
-    sc = wl["scene"]
-    w, h, iters = sc["width"], sc["height"], sc["iters"]
-    vol, opts, mcs = build_scene(**sc)
-    # host-side inputs of the end-to-end arm live in pinned memory
-    vol_pinned = torch.from_numpy(np.ascontiguousarray(vol)).pin_memory()
-    vol_host = vol_pinned.numpy()
-    mcs_pinned = [torch.from_numpy(np.ascontiguousarray(m)).pin_memory() for m in mcs]
-    mcs_host = [m.numpy() for m in mcs_pinned]
-
-    layout = ShardLayout(w, h, world, *TILE)
-    r = Renderer(local)
-    r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2, "wave": 3, "bricks": 4}[args.kernel])
-    for kv in args.opt:
-        k, v = kv.split("=")
-        r.set_option(int(k), int(v))
-    r.set_tile_shard(rank, world, *TILE)
-    stream = torch.cuda.Stream(device=dev)
-    r.set_stream(stream.cuda_stream)
-    gather = FrameGatherer(layout, rank, dev, torch.int32, renderer=r) if world > 1 else None
-    frame1 = torch.empty(w * h, dtype=torch.int32, device=dev) if world == 1 else None
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    argb_host = torch.empty(w * h, dtype=torch.int32).pin_memory()
-    # the default kernel writes the ARGB words while it renders: straight into the buffer the frame is
-    # assembled from (the gather's send buffer when sharded), so that TonemapImage costs no extra pass
-    if world == 1:
-        r.set_argb_target(frame1.data_ptr(), packed=False)
-    else:
-        r.set_argb_target(gather.local.data_ptr(), packed=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def resident_frame():
-        """all passes + tonemap (+ gather) from inputs resident in HBM; returns the frame on rank 0"""
-        r.clear_accum(w, h)
-        r.render_resident(0, iters)
-        if world == 1:
-            r.tonemap_device(opts[0], frame1.data_ptr(), packed=False)
-            return frame1
-        r.tonemap_device(opts[0], gather.local.data_ptr(), packed=True)
-        return gather.gather()
-
-    # ---- inputs into HBM, work count (untimed) ----
-    with torch.cuda.stream(stream):
-        r.set_volume(vol_host)
-        r.clear_accum(w, h)
-        r.upload_passes(opts, mcs)
-        r.reset_stats()
-        r.count_work(True)
-        resident_frame()
-        st = r.stats()
-        r.count_work(False)
-        work = torch.tensor([st["steps"], st["taps"], st["outer_iters"]], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(work)
-        steps_frame, taps_frame, outer_frame = [int(x) for x in work.tolist()]
-
-        # ---- device-resident timed loop ----
-        sampler = ClockSampler(local) if rank == 0 else None  # polling starts during the warm-up
-        for _ in range(args.warmup):
-            resident_frame()
-            flush.zero_()
-        barrier()
-        r.reset_stats()
-        t_wall0 = time.perf_counter()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b in ev:
-            a.record(stream)
-            resident_frame()
-            b.record(stream)
-            flush.zero_()  # L2 flush between timed iterations, outside the event pair
-        barrier()
-        t_wall1 = time.perf_counter()
-        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-        st = r.stats()
-        t = torch.tensor([dev_ms, st["render_ms"]], dtype=torch.float64, device=dev)
-        launches = torch.tensor([st["kernel_launches"]], dtype=torch.int64, device=dev)
-        per_rank = [t.clone() for _ in range(world)]
-        if world > 1:
-            dist.all_gather(per_rank, t)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(launches)
-        dev_ms, render_ms = t.tolist()
-        rank_render_ms = [float(x[1]) / args.steps for x in per_rank]
-        rank_step_ms = [float(x[0]) / args.steps for x in per_rank]
-
-        # ---- parity of the frame that was just timed (production kernel, last timed step) ----
-        parity = None
-        if not args.no_parity:
-            accum_last = r.read_accum()
-            if world == 1:
-                argb_last = frame1.cpu().numpy().view(np.uint32)
-            else:
-                fr = resident_frame()
-                argb_last = fr.cpu().numpy().view(np.uint32) if rank == 0 else None
-            from oracle import build_oracle, refso
-            build_oracle.build(verbose=False)
-            orc = refso.load("oracle")
-            stride = 64 if w * h * iters > 4_000_000 else 1
-            if rank == 0:
-                parity = parity_check(orc, vol, mcs, opts, w, h, accum_last, argb_last, stride)
-            ok, npx = counters_check(r, orc, vol, mcs, opts, w, h, iters, rank, world, resident_frame) if rank == 0 else (True, 0)
-            if rank == 0:
-                parity["counters_exact"] = bool(ok)
-                parity["counters_pixels"] = npx
-                parity["checker"] = "oracle/rm_oracle.c (strict fp32 restatement, pinned to the reference text)"
-            barrier()
-
-        # ---- end to end through the host-buffer calls ----
-        e2e = None
-        if not args.no_e2e:
-            if world == 1:
-                r.set_argb_target(None)  # rm_tonemap reads the context's own frame, which the render launch then fills
-
-            def host_frame():
-                r.set_volume(vol_host)
-                r.clear_accum(w, h)
-                r.render_frame(opts, mcs_host)
-                if world == 1:
-                    return r.tonemap(opts[0], out=argb_host.numpy().view(np.uint32))
-                r.tonemap_device(opts[0], gather.local.data_ptr(), packed=True)
-                fr = gather.gather()
-                if rank == 0:
-                    argb_host.copy_(fr, non_blocking=True)
-                    torch.cuda.current_stream().synchronize()
-                return None
-
-            for _ in range(max(1, min(args.warmup, 3))):
-                host_frame()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                host_frame()
-            barrier()
-            e2e_s = time.perf_counter() - t0
-            te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            e2e_s = te.item()
-            h2d = vol.size + iters * (65536 * 4 + 544)
-            e2e = {"value": steps_frame * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s",
-                   "frames_per_s": args.steps / e2e_s, "ms_per_step": 1e3 * e2e_s / args.steps,
-                   "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(w * h * 4),
-                   "path": "rm_set_volume + rm_clear_accum + rm_render_frame + rm_tonemap, pinned host buffers"
-                           + ("" if world == 1 else "; every rank uploads its own copy of the inputs")}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    ms_per_step = dev_ms / args.steps
-    value = steps_frame / (ms_per_step * 1e-3) / 1e6
-    peak, peak_src = peaks()
-    # per launch of the render kernel: frame bytes / launches-per-frame over avg launch duration
-    kernel_s_per_frame = render_ms * 1e-3 / args.steps
-    achieved = (steps_frame / world + taps_frame / world) / kernel_s_per_frame / 1e9  # per GPU
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic(args.workload, args.kernel),
-            "peak_source": peak_src,
-            "kernel": {"fast": "k_render_bricks (all passes of a frame in one launch)",
-                       "warp": "k_render_warp (persistent, all passes of a frame in one launch)",
-                       "wave": "k_wave_* pipeline (primary, prepare / persistent trace per level, final)",
-                       "plain": "k_render_plain (one launch per pass)"}[args.kernel],
-            "algorithmic_bytes_per_frame": steps_frame + taps_frame,
-            "kernel_ms_per_frame": kernel_s_per_frame * 1e3,
-            "kernel_share_of_step": kernel_s_per_frame * 1e3 / ms_per_step,
-            "note": "1 B per reference-equivalent voxel fetch (inner steps + occupancy taps). The volume and its "
-                    "derived tables are L1/L2-resident and most fetches are elided, so DRAM traffic stays far below "
-                    "the algorithmic bytes by design; the kernel is instruction-issue bound (DESIGN.md 4-5)"}
 
     line = {
         "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world,

@@ -85,13 +85,28 @@ typedef enum rm_option {
   RM_OPT_WAVE_CHUNK = 8,   /* kernel 3: (pixel, pass) items per chunk of the pipeline (1024..2^24, default 2^24) */
   RM_OPT_WAVE_REFILL = 9,  /* kernel 3: the trace kernel hands new rays to idle lanes once this many lanes of a
                               warp are idle (1 = at once ... 32 = the warp starts 32 rays together) */
-  RM_OPT_PERSIST_BLOCK = 10 /* kernel 0: threads of the one resident block per SM: 0 = default, 512, 768, 1024 */
+  RM_OPT_PERSIST_BLOCK = 10, /* kernel 0: threads of the one resident block per SM: 0 = default, 512, 768, 1024 */
+  RM_OPT_PERSIST_GROUP = 11  /* kernel 0: warps that draw their work bundles together and meet at a barrier per draw
+                               (1 = every warp free-running; rounded down to a divisor of the block's warps, <= 15) */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */
 int  rm_abi_version(void);
 int  rm_device_count(void);
 int  rm_create(int device_id, rm_ctx** out_ctx);
+/* One context over the n GPUs device_ids[0..n-1] of a box (the reference is single-device: cl/max-device,
+ * core.clj:121-123 -- a host changes exactly that one call site). The context takes every call of this
+ * header that is not marked single-GPU: inputs are uploaded once and broadcast device-to-device, image tiles
+ * are dealt to the GPUs (diagonal stripes of 16x8 tiles), every GPU's render kernel stores the ARGB words of
+ * its tiles directly into device_ids[0]'s frame over NVLink, and rm_tonemap reads that frame back. Needs peer
+ * access from every device to device_ids[0] (NVSwitch boxes have it); RM_ERR_UNSUPPORTED otherwise.
+ * Single-GPU only: rm_set_stream, rm_tonemap_device, rm_copy_accum_device, rm_set_argb_target,
+ * rm_unpack_shards; rm_set_tile_shard(ctx, 0, 1, w, h) sets the tile size. */
+int  rm_create_multi(const int* device_ids, int n, rm_ctx** out_ctx);
+/* GPUs behind a context (1 for rm_create), and the stats of one of them (rm_get_stats on a multi-GPU
+ * context sums the work and takes the slowest member's times). */
+int  rm_member_count(const rm_ctx* ctx);
+int  rm_get_member_stats(const rm_ctx* ctx, int member, rm_stats* out);
 void rm_destroy(rm_ctx* ctx);
 const char* rm_last_error(const rm_ctx* ctx);
 

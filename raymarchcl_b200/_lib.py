@@ -25,6 +25,7 @@ RM_OPT_TRIP_LIMIT = 7
 RM_OPT_WAVE_CHUNK = 8
 RM_OPT_WAVE_REFILL = 9
 RM_OPT_PERSIST_BLOCK = 10
+RM_OPT_PERSIST_GROUP = 11
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
@@ -32,7 +33,7 @@ EXPORTS = [
     "rm_clear_accum", "rm_render_pass", "rm_render_frame", "rm_tonemap", "rm_read_accum",
     "rm_upload_passes", "rm_render_resident", "rm_tonemap_device", "rm_copy_accum_device", "rm_sync",
     "rm_set_stream", "rm_set_tile_shard", "rm_shard_pixels", "rm_shard_slots", "rm_unpack_shards", "rm_set_option", "rm_get_stats",
-    "rm_reset_stats", "rm_set_volume_device", "rm_tonemap_async", "rm_wait", "rm_update_opts", "rm_set_argb_target", "rm_host_alloc", "rm_host_free",
+    "rm_reset_stats", "rm_set_volume_device", "rm_tonemap_async", "rm_wait", "rm_update_opts", "rm_set_argb_target", "rm_host_alloc", "rm_host_free", "rm_create_multi", "rm_member_count", "rm_get_member_stats",
 ]
 
 
@@ -109,5 +110,8 @@ def load() -> C.CDLL:
     lib.rm_set_argb_target.argtypes = [vp, vp, ip]
     lib.rm_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     lib.rm_host_free.argtypes = [vp, vp]
+    lib.rm_create_multi.argtypes = [C.POINTER(ip), ip, C.POINTER(vp)]
+    lib.rm_member_count.argtypes = [vp]
+    lib.rm_get_member_stats.argtypes = [vp, ip, C.POINTER(RmStats)]
     _lib = lib
     return lib

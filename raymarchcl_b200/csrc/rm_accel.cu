@@ -159,11 +159,11 @@ cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso
   const unsigned nib_bytes = (unsigned)(((nc + 1) / 2 + 15) & ~(size_t)15);
   k_pack_nibbles<<<(nib_bytes + 255) / 256, 256, 0, stream>>>(st->d_tmp, (long long)nc, st->d_nib, nib_bytes);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  unsigned differ = 1;
-  if ((e = cudaMemcpyAsync(&differ, st->d_flag, sizeof differ, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+  // (round 1 read the `differ` flag back here to alias occ to solid when no voxel equals isoVal; that
+  //  cost a stream synchronisation on every upload -- the build is now fully asynchronous and the normal
+  //  taps, a few dozen per pixel-sample, always read the occ bricks)
   a.solid = st->d_solid;
-  a.occ = differ ? st->d_occ : st->d_solid;  // identical predicates unless some voxel == isoVal
+  a.occ = st->d_occ;
   a.dist = st->d_tmp;
   a.nib = st->d_nib;
   a.nib_bytes = nib_bytes;

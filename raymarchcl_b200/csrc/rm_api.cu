@@ -77,6 +77,7 @@ struct rm_ctx {
   unsigned long long* d_queue = nullptr;  // [0] work queue head of the warp kernel, [1] bundle tickets of the default kernel
   unsigned long long queue_base = 0;      // expected value of d_queue[1] (monotonic, rm_launch_render_persist)
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
+  int persist_group = 1;                  // warps of the default kernel that draw bundles together (RM_OPT_PERSIST_GROUP)
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
   int warp_blocks[2] = {0, 0};            // resident blocks per SM of the warp kernel [plain, counting]
@@ -88,7 +89,44 @@ struct rm_ctx {
 
   rm_stats stats{};
   std::vector<EventPair> pending, free_events;
+
+  // rm_create_multi: a group context owns one member context per GPU and forwards every call
+  std::vector<rm_ctx*> members;
+  bool is_group = false;
 };
+
+// group (multi-GPU) forms of the public calls, defined at the end of this file
+namespace grp {
+int set_volume(rm_ctx* g, const uint8_t* voxels, int rx, int ry, int rz);
+int set_volume_device(rm_ctx* g, const void* d_voxels, int rx, int ry, int rz);
+int load_volume_file(rm_ctx* g, const char* path, int* rx, int* ry, int* rz);
+int generate_volume(rm_ctx* g, int kind, int rx, int ry, int rz);
+int voxelize_points(rm_ctx* g, const float* xyz, int64_t n, int res, int ks);
+int clear_accum(rm_ctx* g, int w, int h);
+int render_frame(rm_ctx* g, const void* const* opts, const float* const* mc, int iter);
+int tonemap(rm_ctx* g, const void* opts, size_t len, uint32_t* out, int async_slot);
+int wait(rm_ctx* g, int slot);
+int read_accum(rm_ctx* g, float* out);
+int get_stats(rm_ctx* g, rm_stats* out);
+int set_tile(rm_ctx* g, int tile_w, int tile_h);
+void destroy(rm_ctx* g);
+int member_failed(rm_ctx* g, rm_ctx* m, int rc);
+int unsupported(rm_ctx* g, const char* what);
+}  // namespace grp
+
+// Forwards a call to every member of a group; `m` names the member inside CALL. Calls that are
+// asynchronous on one GPU stay asynchronous, so the GPUs of a group work concurrently.
+#define RM_FORWARD(c, CALL)                                        \
+  do {                                                             \
+    if ((c)->is_group) {                                           \
+      for (rm_ctx* m : (c)->members) {                             \
+        const int rc__ = (CALL);                                   \
+        if (rc__) return grp::member_failed((c), m, rc__);         \
+      }                                                            \
+      return RM_OK;                                                \
+    }                                                              \
+  } while (0)
+
 
 namespace {
 
@@ -162,11 +200,7 @@ void update_shard(rm_ctx* c) {
   RmShard& s = c->shard;
   s.rank = c->shard_rank; s.world = c->shard_world;
   s.tile_w = c->shard_tw; s.tile_h = c->shard_th;
-  s.tiles_x = c->W > 0 ? (c->W + s.tile_w - 1) / s.tile_w : 0;
-  s.tiles_y = c->H > 0 ? (c->H + s.tile_h - 1) / s.tile_h : 0;
-  const long long tiles = (long long)s.tiles_x * s.tiles_y;
-  s.owned_tiles = tiles > s.rank ? (int)((tiles - s.rank + s.world - 1) / s.world) : 0;
-  s.slots = (long long)s.owned_tiles * s.tile_w * s.tile_h;
+  rm_shard_layout(s, c->W, c->H);
 }
 
 int ensure_tables(rm_ctx* c, int n) {
@@ -349,7 +383,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
           int packed = 0;
           uint32_t* argb = fused_argb_target(c, &packed);
           e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
-                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, c->persist_block, c->stream);
+                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, c->persist_block, c->persist_group, c->stream);
           launched = 1;
           if (e == cudaSuccess && argb) {
             c->argb_fresh_ptr = argb;
@@ -477,6 +511,7 @@ int rm_create(int device_id, rm_ctx** out_ctx) {
 
 void rm_destroy(rm_ctx* c) {
   if (!c) return;
+  if (c->is_group) { grp::destroy(c); return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -498,6 +533,7 @@ void rm_destroy(rm_ctx* c) {
 
 int rm_set_volume(rm_ctx* c, const uint8_t* voxels, int rx, int ry, int rz) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::set_volume(c, voxels, rx, ry, rz);
   if (!voxels || rx <= 0 || ry <= 0 || rz <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: null volume or non-positive extent");
   if ((long long)rx * ry > 0x7fffffffLL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume: rx*ry overflows int (voxelRes.w)");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -518,6 +554,7 @@ int rm_set_volume(rm_ctx* c, const uint8_t* voxels, int rx, int ry, int rz) {
 // another kernel): one device-to-device copy on the context's stream, no host traffic.
 int rm_set_volume_device(rm_ctx* c, const void* d_voxels, int rx, int ry, int rz) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::set_volume_device(c, d_voxels, rx, ry, rz);
   if (!d_voxels || rx <= 0 || ry <= 0 || rz <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume_device: null volume or non-positive extent");
   if ((long long)rx * ry > 0x7fffffffLL) return fail(c, RM_ERR_INVALID_ARG, "rm_set_volume_device: rx*ry overflows int (voxelRes.w)");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -533,6 +570,7 @@ int rm_set_volume_device(rm_ctx* c, const void* d_voxels, int rx, int ry, int rz
 // (save-volume / load-volume, io.clj:9-33).
 int rm_load_volume_file(rm_ctx* c, const char* path, int* out_rx, int* out_ry, int* out_rz) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::load_volume_file(c, path, out_rx, out_ry, out_rz);
   if (!path) return fail(c, RM_ERR_INVALID_ARG, "rm_load_volume_file: null path");
   std::FILE* f = std::fopen(path, "rb");
   if (!f) return fail(c, RM_ERR_IO, std::string("rm_load_volume_file: cannot open ") + path);
@@ -571,6 +609,7 @@ int rm_load_volume_file(rm_ctx* c, const char* path, int* out_rx, int* out_ry, i
 // make-gyroid-volume on the device (generators.clj:27-42); replaces rm_set_volume for that volume.
 int rm_generate_gyroid_volume(rm_ctx* c, int rx, int ry, int rz) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::generate_volume(c, 0, rx, ry, rz);
   if (rx <= 0 || ry <= 0 || rz <= 0 || (long long)rx * ry > 0x7fffffffLL)
     return fail(c, RM_ERR_INVALID_ARG, "rm_generate_gyroid_volume: bad extents");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -591,6 +630,7 @@ int rm_generate_gyroid_volume(rm_ctx* c, int rx, int ry, int rz) {
 // gen/make-terrain (generators.clj:44-60) on the device.
 int rm_generate_terrain_volume(rm_ctx* c, int rx, int ry, int rz) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::generate_volume(c, 1, rx, ry, rz);
   if (rx <= 0 || ry <= 0 || rz < rx || (long long)rx * ry > 0x7fffffffLL)  // the reference's second wall needs rz >= rx
     return fail(c, RM_ERR_INVALID_ARG, "rm_generate_terrain_volume: bad extents");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -613,6 +653,7 @@ int rm_generate_terrain_volume(rm_ctx* c, int rx, int ry, int rz) {
 // are scaled into the res^3 grid like mesh-scale (:16-23) and splatted with value 255.
 int rm_voxelize_points(rm_ctx* c, const float* xyz, int64_t n_points, int res, int ks) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::voxelize_points(c, xyz, n_points, res, ks);
   if (!xyz || n_points <= 0 || n_points > (1ll << 40)) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: null points or bad count");
   if (res <= 0 || res > 2048 || ks > 64) return fail(c, RM_ERR_INVALID_ARG, "rm_voxelize_points: res must be 1..2048 and ks <= 64");
   // the splat kernel runs one thread per (point, x-offset of the dilation cube): its 256-thread block count must fit a grid
@@ -644,6 +685,7 @@ int rm_voxelize_points(rm_ctx* c, const float* xyz, int64_t n_points, int res, i
 // Parity hook: read the resident volume back.
 int rm_read_volume(rm_ctx* c, uint8_t* voxels_out) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return rm_read_volume(c->members[0], voxels_out);
   if (!voxels_out) return fail(c, RM_ERR_INVALID_ARG, "rm_read_volume: null output");
   if (!c->d_vox || c->rx <= 0) return fail(c, RM_ERR_NO_VOLUME, "no volume uploaded (rm_set_volume)");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -658,6 +700,7 @@ int rm_read_volume(rm_ctx* c, uint8_t* voxels_out) {
 // slots 0 .. count-1; rm_upload_passes(ctx, opts, NULL, iter) then uses them.
 int rm_generate_scatter_tables(rm_ctx* c, int64_t seed0, int count) {
   if (!c) return RM_ERR_INVALID_ARG;
+  RM_FORWARD(c, rm_generate_scatter_tables(m, seed0, count));
   if (count <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_generate_scatter_tables: count <= 0");
   RM_CUDA(c, cudaSetDevice(c->device));
   if (c->table_capacity < count) RM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -673,6 +716,7 @@ int rm_generate_scatter_tables(rm_ctx* c, int64_t seed0, int count) {
 
 int rm_clear_accum(rm_ctx* c, int width, int height) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::clear_accum(c, width, height);
   if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL / 37)
     return fail(c, RM_ERR_INVALID_ARG, "rm_clear_accum: bad framebuffer extent");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -703,8 +747,11 @@ int rm_render_pass(rm_ctx* c, const void* opts, size_t opts_len, const float* mc
   return rm_render_frame(c, o, m, 1);
 }
 
-int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
-  if (!c) return RM_ERR_INVALID_ARG;
+// Queue all passes of a frame on the context's stream (no synchronisation). The tables come from the
+// caller's host buffers, or -- peer_src != null, multi-GPU groups -- from the table slots of another
+// member over NVLink once `src_ready` has fired there.
+static int queue_frame(rm_ctx* c, const void* const* opts, const float* const* mc, int iter, const rm_ctx* peer_src,
+                       cudaEvent_t src_ready, cudaEvent_t uploaded = nullptr) {
   if (!opts || !mc || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_render_frame: null arrays or iter <= 0");
   int rc = require_ready(c);
   if (rc) return rc;
@@ -724,18 +771,34 @@ int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, 
   c->generated_tables = 0;
   EventPair t = begin_timed(c, 2);
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < iter && e == cudaSuccess; ++i)  // straight from the caller's (ideally pinned) buffers
-    e = cudaMemcpyAsync(c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4), mc[i], tbytes, cudaMemcpyHostToDevice, c->stream);
+  if (peer_src) {
+    e = cudaStreamWaitEvent(c->stream, src_ready, 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeerAsync(c->d_tables, c->device, peer_src->d_tables, peer_src->device, tbytes * iter, c->stream);
+  } else {
+    for (int i = 0; i < iter && e == cudaSuccess; ++i)  // straight from the caller's (ideally pinned) buffers
+      e = cudaMemcpyAsync(c->d_tables + (size_t)i * (RM_TABLE_FLOATS / 4), mc[i], tbytes, cudaMemcpyHostToDevice, c->stream);
+    c->stats.h2d_bytes += tbytes * iter;
+  }
   end_timed(c, t);
+  if (e == cudaSuccess && uploaded) e = cudaEventRecord(uploaded, c->stream);  // the tables are in place from here on
   if (e != cudaSuccess) return cuda_fail(c, e, "table upload");
-  c->stats.h2d_bytes += tbytes * iter + (size_t)RM_OPTS_BYTES * iter;
-  if ((rc = launch_passes(c, dec.data(), iter, c->d_tables))) return rc;
+  c->stats.h2d_bytes += (size_t)RM_OPTS_BYTES * iter;
+  return launch_passes(c, dec.data(), iter, c->d_tables);
+}
+
+int rm_render_frame(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
+  if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::render_frame(c, opts, mc, iter);
+  int rc = queue_frame(c, opts, mc, iter, nullptr, nullptr);
+  if (rc) return rc;
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   return check_watchdog(c);
 }
 
 int rm_upload_passes(rm_ctx* c, const void* const* opts, const float* const* mc, int iter) {
   if (!c) return RM_ERR_INVALID_ARG;
+  RM_FORWARD(c, rm_upload_passes(m, opts, mc, iter));
   if (!opts || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: null opts array or iter <= 0");
   if (!mc && iter > c->generated_tables)
     return fail(c, RM_ERR_INVALID_ARG, "rm_upload_passes: mc == NULL needs rm_generate_scatter_tables(count >= iter) first");
@@ -769,6 +832,7 @@ int rm_upload_passes(rm_ctx* c, const void* const* opts, const float* const* mc,
 // uploaded passes (a new camera, say); the tables stay where they are. 544 bytes per pass of host traffic.
 int rm_update_opts(rm_ctx* c, const void* const* opts, int iter) {
   if (!c) return RM_ERR_INVALID_ARG;
+  RM_FORWARD(c, rm_update_opts(m, opts, iter));
   if (!opts || iter <= 0) return fail(c, RM_ERR_INVALID_ARG, "rm_update_opts: null opts array or iter <= 0");
   if (iter != c->resident) return fail(c, RM_ERR_INVALID_ARG, "rm_update_opts: iter differs from the passes uploaded by rm_upload_passes");
   int rc = require_ready(c);
@@ -787,6 +851,7 @@ int rm_update_opts(rm_ctx* c, const void* const* opts, int iter) {
 
 int rm_render_resident(rm_ctx* c, int first, int count) {
   if (!c) return RM_ERR_INVALID_ARG;
+  RM_FORWARD(c, rm_render_resident(m, first, count));
   int rc = require_ready(c);
   if (rc) return rc;
   if (first < 0 || count <= 0 || first + count > c->resident)
@@ -813,11 +878,15 @@ static int tonemap_into_frame(rm_ctx* c, const RmOpts& o) {
   end_timed(c, t);
   if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
   c->stats.kernel_launches += 1;
+  c->argb_fresh_ptr = frame;  // the frame now holds TonemapImage(accumulator, this gamma)
+  c->argb_fresh_packed = 0;
+  c->argb_fresh_gamma = o.gamma;
   return RM_OK;
 }
 
 int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::tonemap(c, opts, opts_len, argb_out, -1);
   if (!opts || opts_len != RM_OPTS_BYTES || !argb_out) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap: bad opts blob or null output");
   if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -843,6 +912,7 @@ int rm_tonemap(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out)
 // slot (0 or 1) names the transfer for rm_wait.
 int rm_tonemap_async(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* argb_out, int slot) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return (slot < 0 || slot > 1) ? fail(c, RM_ERR_INVALID_ARG, "rm_tonemap_async: slot must be 0 or 1") : grp::tonemap(c, opts, opts_len, argb_out, slot);
   if (!opts || opts_len != RM_OPTS_BYTES || !argb_out) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap_async: bad opts blob or null output");
   if (slot < 0 || slot > 1) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap_async: slot must be 0 or 1");
   if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
@@ -877,6 +947,7 @@ int rm_tonemap_async(rm_ctx* c, const void* opts, size_t opts_len, uint32_t* arg
 // Block until the transfer started by rm_tonemap_async(.., slot) has landed in host memory.
 int rm_wait(rm_ctx* c, int slot) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::wait(c, slot);
   if (slot < 0 || slot > 1) return fail(c, RM_ERR_INVALID_ARG, "rm_wait: slot must be 0 or 1");
   if (!c->copy_pending[slot]) return RM_OK;
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -887,6 +958,7 @@ int rm_wait(rm_ctx* c, int slot) {
 
 int rm_host_alloc(rm_ctx* c, size_t bytes, void** out_ptr) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return rm_host_alloc(c->members[0], bytes, out_ptr);
   if (!out_ptr || bytes == 0) return fail(c, RM_ERR_INVALID_ARG, "rm_host_alloc: null out pointer or zero size");
   *out_ptr = nullptr;
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -896,6 +968,7 @@ int rm_host_alloc(rm_ctx* c, size_t bytes, void** out_ptr) {
 
 int rm_host_free(rm_ctx* c, void* ptr) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return rm_host_free(c->members[0], ptr);
   if (!ptr) return RM_OK;
   RM_CUDA(c, cudaSetDevice(c->device));
   for (int s2 = 0; s2 < 2; ++s2)  // a transfer into it may still be in flight
@@ -906,6 +979,7 @@ int rm_host_free(rm_ctx* c, void* ptr) {
 
 int rm_tonemap_device(rm_ctx* c, const void* opts, size_t opts_len, void* d_argb, int packed) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::unsupported(c, "rm_tonemap_device");
   if (!opts || opts_len != RM_OPTS_BYTES || !d_argb) return fail(c, RM_ERR_INVALID_ARG, "rm_tonemap_device: bad opts blob or null output");
   if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -918,6 +992,9 @@ int rm_tonemap_device(rm_ctx* c, const void* opts, size_t opts_len, void* d_argb
   end_timed(c, t);
   if (e != cudaSuccess) return cuda_fail(c, e, "tonemap kernel launch");
   c->stats.kernel_launches += 1;
+  c->argb_fresh_ptr = d_argb;  // (whatever the render launch left in this or another buffer is no longer "the" frame)
+  c->argb_fresh_packed = packed != 0;
+  c->argb_fresh_gamma = o.gamma;
   return RM_OK;
 }
 
@@ -928,6 +1005,7 @@ int rm_tonemap_device(rm_ctx* c, const void* opts, size_t opts_len, void* d_argb
 // one frame. NULL restores the context's own frame.
 int rm_set_argb_target(rm_ctx* c, void* d_argb, int packed) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::unsupported(c, "rm_set_argb_target");
   c->argb_target = static_cast<uint32_t*>(d_argb);
   c->argb_target_packed = d_argb ? (packed != 0) : 0;
   c->argb_fresh_ptr = nullptr;
@@ -936,6 +1014,7 @@ int rm_set_argb_target(rm_ctx* c, void* d_argb, int packed) {
 
 int rm_copy_accum_device(rm_ctx* c, void* d_rgba, int packed) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::unsupported(c, "rm_copy_accum_device");
   if (!d_rgba) return fail(c, RM_ERR_INVALID_ARG, "rm_copy_accum_device: null output");
   if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -951,6 +1030,7 @@ int rm_copy_accum_device(rm_ctx* c, void* d_rgba, int packed) {
 
 int rm_read_accum(rm_ctx* c, float* rgba_out) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::read_accum(c, rgba_out);
   if (!rgba_out) return fail(c, RM_ERR_INVALID_ARG, "rm_read_accum: null output");
   if (!c->d_accum) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
   RM_CUDA(c, cudaSetDevice(c->device));
@@ -963,6 +1043,7 @@ int rm_read_accum(rm_ctx* c, float* rgba_out) {
 
 int rm_sync(rm_ctx* c) {
   if (!c) return RM_ERR_INVALID_ARG;
+  RM_FORWARD(c, rm_sync(m));
   RM_CUDA(c, cudaSetDevice(c->device));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   return check_watchdog(c);
@@ -970,6 +1051,7 @@ int rm_sync(rm_ctx* c) {
 
 int rm_set_stream(rm_ctx* c, void* cuda_stream) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::unsupported(c, "rm_set_stream");
   RM_CUDA(c, cudaSetDevice(c->device));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   resolve_timers(c);
@@ -979,6 +1061,7 @@ int rm_set_stream(rm_ctx* c, void* cuda_stream) {
 
 int rm_set_tile_shard(rm_ctx* c, int rank, int world, int tile_w, int tile_h) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return (rank != 0 || world != 1) ? fail(c, RM_ERR_INVALID_ARG, "rm_set_tile_shard on a multi-GPU context: rank 0, world 1 (only the tile size is taken)") : grp::set_tile(c, tile_w, tile_h);
   if (world <= 0 || rank < 0 || rank >= world || tile_w <= 0 || tile_h <= 0 || (tile_w & 7) || (tile_h & 3))
     return fail(c, RM_ERR_INVALID_ARG, "rm_set_tile_shard: need 0 <= rank < world, tile_w % 8 == 0, tile_h % 4 == 0");
   c->shard_rank = rank; c->shard_world = world; c->shard_tw = tile_w; c->shard_th = tile_h;
@@ -988,14 +1071,17 @@ int rm_set_tile_shard(rm_ctx* c, int rank, int world, int tile_w, int tile_h) {
 }
 
 int64_t rm_shard_slots(const rm_ctx* c, int rank, int world) {
+  if (c && c->is_group) c = c->members[0];
   if (!c || c->W <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
-  const long long tiles = (long long)c->shard.tiles_x * c->shard.tiles_y;
-  const long long owned = tiles > rank ? (tiles - rank + world - 1) / world : 0;
-  return owned * c->shard.tile_w * c->shard.tile_h;
+  RmShard s = c->shard;
+  s.rank = rank; s.world = world;
+  rm_shard_layout(s, c->W, c->H);
+  return s.slots;  // the same for every rank of a world: tiles_per_rank_row x tiles_y tiles, padding included
 }
 
 int rm_unpack_shards(rm_ctx* c, const void* d_parts, int world, int64_t stride_slots, int elem_bytes, void* d_frame) {
   if (!c) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::unsupported(c, "rm_unpack_shards");
   if (!d_parts || !d_frame || world <= 0 || (elem_bytes != 4 && elem_bytes != 16))
     return fail(c, RM_ERR_INVALID_ARG, "rm_unpack_shards: null buffer, world <= 0 or element size not 4 / 16");
   if (c->W <= 0) return fail(c, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
@@ -1009,21 +1095,29 @@ int rm_unpack_shards(rm_ctx* c, const void* d_parts, int world, int64_t stride_s
 }
 
 int64_t rm_shard_pixels(const rm_ctx* c) {
+  if (c && c->is_group) {
+    int64_t px = 0;
+    for (const rm_ctx* m : c->members) px += rm_shard_pixels(m);
+    return px;
+  }
   if (!c || c->W <= 0) return 0;
   const RmShard& s = c->shard;
   int64_t px = 0;
-  for (long long lt = 0; lt < s.owned_tiles; ++lt) {
-    const long long t = lt * s.world + s.rank;
-    const int ty = (int)(t / s.tiles_x), tx = (int)(t % s.tiles_x);
-    const int w = (tx + 1) * s.tile_w <= c->W ? s.tile_w : c->W - tx * s.tile_w;
+  for (int ty = 0; ty < s.tiles_y; ++ty) {
+    int first = (s.rank - (int)(((long long)s.skew * ty) % s.world)) % s.world;
+    if (first < 0) first += s.world;
     const int h = (ty + 1) * s.tile_h <= c->H ? s.tile_h : c->H - ty * s.tile_h;
-    px += (int64_t)w * h;
+    for (int tx = first; tx < s.tiles_x; tx += s.world) {
+      const int w = (tx + 1) * s.tile_w <= c->W ? s.tile_w : c->W - tx * s.tile_w;
+      px += (int64_t)w * h;
+    }
   }
   return px;
 }
 
 int rm_set_option(rm_ctx* c, int option, int64_t value) {
   if (!c) return RM_ERR_INVALID_ARG;
+  RM_FORWARD(c, rm_set_option(m, option, value));
   switch (option) {
     case RM_OPT_COUNT_WORK: c->count_work = value != 0; return RM_OK;
     case RM_OPT_KERNEL:
@@ -1052,6 +1146,10 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
         return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 512, 768 or 1024 threads");
       c->persist_block = (int)value;
       return RM_OK;
+    case RM_OPT_PERSIST_GROUP:
+      if (value < 1 || value > 32) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_GROUP: 1..32 warps");
+      c->persist_group = (int)value;
+      return RM_OK;
     case RM_OPT_FUSE_LIMIT:
       if (value < 1 || value > RM_MAX_FUSED_PASSES) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_FUSE_LIMIT: 1..32");
       c->fuse_limit = (int)value;
@@ -1063,6 +1161,7 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
 int rm_get_stats(const rm_ctx* cc, rm_stats* out) {
   rm_ctx* c = const_cast<rm_ctx*>(cc);
   if (!c || !out) return RM_ERR_INVALID_ARG;
+  if (c->is_group) return grp::get_stats(c, out);
   RM_CUDA(c, cudaSetDevice(c->device));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   resolve_timers(c);
@@ -1075,6 +1174,7 @@ int rm_get_stats(const rm_ctx* cc, rm_stats* out) {
 
 int rm_reset_stats(rm_ctx* c) {
   if (!c) return RM_ERR_INVALID_ARG;
+  RM_FORWARD(c, rm_reset_stats(m));
   RM_CUDA(c, cudaSetDevice(c->device));
   RM_CUDA(c, cudaStreamSynchronize(c->stream));
   resolve_timers(c);
@@ -1083,4 +1183,282 @@ int rm_reset_stats(rm_ctx* c) {
   return RM_OK;
 }
 
+
+int rm_create_multi(const int* device_ids, int n, rm_ctx** out_ctx) {
+  if (!out_ctx) return fail(nullptr, RM_ERR_INVALID_ARG, "rm_create_multi: out_ctx is null");
+  *out_ctx = nullptr;
+  if (!device_ids || n <= 0 || n > 64) return fail(nullptr, RM_ERR_INVALID_ARG, "rm_create_multi: need 1..64 device ids");
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j)
+      if (device_ids[i] == device_ids[j]) return fail(nullptr, RM_ERR_INVALID_ARG, "rm_create_multi: duplicate device id");
+  rm_ctx* g = new (std::nothrow) rm_ctx();
+  if (!g) return fail(nullptr, RM_ERR_INVALID_ARG, "out of host memory");
+  g->is_group = true;
+  g->device = device_ids[0];
+  for (int i = 0; i < n; ++i) {
+    rm_ctx* m = nullptr;
+    const int rc = rm_create(device_ids[i], &m);
+    if (rc) { grp::destroy(g); return rc; }
+    g->members.push_back(m);
+  }
+  // every GPU stores its tiles of the ARGB frame straight into device_ids[0]'s memory (NVLink / NVSwitch)
+  for (int i = 1; i < n; ++i) {
+    int can = 0;
+    cudaError_t e = cudaSetDevice(device_ids[i]);
+    if (e == cudaSuccess) e = cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[0]);
+    if (e != cudaSuccess || !can) {
+      grp::destroy(g);
+      return fail(nullptr, RM_ERR_UNSUPPORTED, "rm_create_multi: device " + std::to_string(device_ids[i]) +
+                                                   " has no peer access to device " + std::to_string(device_ids[0]));
+    }
+    e = cudaDeviceEnablePeerAccess(device_ids[0], 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    if (e == cudaSuccess) {  // and back, so that the volume / table broadcasts go directly as well
+      cudaSetDevice(device_ids[0]);
+      cudaError_t e2 = cudaDeviceEnablePeerAccess(device_ids[i], 0);
+      if (e2 != cudaSuccess) cudaGetLastError();
+    }
+    if (e != cudaSuccess) { grp::destroy(g); return cuda_fail(nullptr, e, "cudaDeviceEnablePeerAccess"); }
+  }
+  g->shard_tw = 16; g->shard_th = 8;  // small tiles: load balance; the skewed ownership keeps them apart
+  grp::set_tile(g, g->shard_tw, g->shard_th);
+  *out_ctx = g;
+  return RM_OK;
+}
+
+int rm_member_count(const rm_ctx* c) { return !c ? 0 : (c->is_group ? (int)c->members.size() : 1); }
+
+int rm_get_member_stats(const rm_ctx* c, int member, rm_stats* out) {
+  if (!c || !out) return RM_ERR_INVALID_ARG;
+  if (!c->is_group) return member == 0 ? rm_get_stats(c, out) : RM_ERR_INVALID_ARG;
+  if (member < 0 || member >= (int)c->members.size()) return RM_ERR_INVALID_ARG;
+  return rm_get_stats(c->members[(size_t)member], out);
+}
+
 }  // extern "C"
+
+// ---- multi-GPU groups ------------------------------------------------------------------------------
+// One process, one member context (own stream) per GPU, image tiles dealt to the members by
+// rm_set_tile_shard(i, n). Inputs are uploaded ONCE (to member 0) and broadcast device-to-device; every
+// member renders its tiles and its kernel stores the ARGB words of those tiles directly into member
+// 0's frame over NVLink (rm_render_persist.cu writes through argb_target): there is no gather step,
+// no packing and no unpack kernel -- the "collective" is the render kernel's own epilogue.
+namespace grp {
+
+int member_failed(rm_ctx* g, rm_ctx* m, int rc) {
+  g->err = "device " + std::to_string(m->device) + ": " + m->err;
+  return rc;
+}
+
+int unsupported(rm_ctx* g, const char* what) {
+  return fail(g, RM_ERR_UNSUPPORTED, std::string(what) + " is not available on a multi-GPU context (use the members' single-GPU form)");
+}
+
+void destroy(rm_ctx* g) {
+  for (rm_ctx* m : g->members) rm_destroy(m);
+  delete g;
+}
+
+// every member writes its ARGB words into member 0's current frame
+static void retarget(rm_ctx* g) {
+  rm_ctx* m0 = g->members[0];
+  for (rm_ctx* m : g->members) {
+    m->argb_target = m0->d_argb2[m0->argb_cur];
+    m->argb_target_packed = 0;
+    m->argb_fresh_ptr = nullptr;
+  }
+}
+
+int set_tile(rm_ctx* g, int tile_w, int tile_h) {
+  const int n = (int)g->members.size();
+  for (int i = 0; i < n; ++i) {
+    const int rc = rm_set_tile_shard(g->members[(size_t)i], i, n, tile_w, tile_h);
+    if (rc) return member_failed(g, g->members[(size_t)i], rc);
+  }
+  g->shard_tw = tile_w; g->shard_th = tile_h;
+  return RM_OK;
+}
+
+// member 0 holds the new volume (possibly still being written on its stream): copy it to the others
+static int broadcast_volume(rm_ctx* g) {
+  rm_ctx* m0 = g->members[0];
+  const size_t bytes = (size_t)m0->rx * m0->ry * m0->rz;
+  RM_CUDA(g, cudaSetDevice(m0->device));
+  RM_CUDA(g, cudaEventRecord(m0->frame_ready[0], m0->stream));
+  for (size_t i = 1; i < g->members.size(); ++i) {
+    rm_ctx* m = g->members[i];
+    RM_CUDA(g, cudaSetDevice(m->device));
+    int rc = begin_volume(m, bytes, "volume broadcast");
+    if (rc) return member_failed(g, m, rc);
+    RM_CUDA(g, cudaStreamWaitEvent(m->stream, m0->frame_ready[0], 0));
+    RM_CUDA(g, cudaMemcpyPeerAsync(m->d_vox, m->device, m0->d_vox, m0->device, bytes, m->stream));
+    commit_volume(m, m0->rx, m0->ry, m0->rz);
+  }
+  return RM_OK;
+}
+
+int set_volume(rm_ctx* g, const uint8_t* voxels, int rx, int ry, int rz) {
+  int rc = rm_set_volume(g->members[0], voxels, rx, ry, rz);  // ONE upload over PCIe ...
+  if (rc) return member_failed(g, g->members[0], rc);
+  return broadcast_volume(g);                                    // ... then NVLink
+}
+
+int set_volume_device(rm_ctx* g, const void* d_voxels, int rx, int ry, int rz) {
+  int rc = rm_set_volume_device(g->members[0], d_voxels, rx, ry, rz);
+  if (rc) return member_failed(g, g->members[0], rc);
+  return broadcast_volume(g);
+}
+
+int load_volume_file(rm_ctx* g, const char* path, int* rx, int* ry, int* rz) {
+  int rc = rm_load_volume_file(g->members[0], path, rx, ry, rz);
+  if (rc) return member_failed(g, g->members[0], rc);
+  return broadcast_volume(g);
+}
+
+int generate_volume(rm_ctx* g, int kind, int rx, int ry, int rz) {
+  rm_ctx* m0 = g->members[0];
+  int rc = kind == 0 ? rm_generate_gyroid_volume(m0, rx, ry, rz) : rm_generate_terrain_volume(m0, rx, ry, rz);
+  if (rc) return member_failed(g, m0, rc);
+  return broadcast_volume(g);
+}
+
+int voxelize_points(rm_ctx* g, const float* xyz, int64_t n, int res, int ks) {
+  int rc = rm_voxelize_points(g->members[0], xyz, n, res, ks);
+  if (rc) return member_failed(g, g->members[0], rc);
+  return broadcast_volume(g);
+}
+
+int clear_accum(rm_ctx* g, int w, int h) {
+  for (rm_ctx* m : g->members) {
+    const int rc = rm_clear_accum(m, w, h);
+    if (rc) return member_failed(g, m, rc);
+  }
+  g->W = w; g->H = h;
+  retarget(g);
+  return RM_OK;
+}
+
+int render_frame(rm_ctx* g, const void* const* opts, const float* const* mc, int iter) {
+  rm_ctx* m0 = g->members[0];
+  // tables: host -> member 0 over PCIe once, then device to device over NVLink (an event marks the upload)
+  int rc = queue_frame(m0, opts, mc, iter, nullptr, nullptr, m0->frame_ready[1]);
+  if (rc) return member_failed(g, m0, rc);
+  for (size_t i = 1; i < g->members.size(); ++i) {
+    rm_ctx* m = g->members[i];
+    rc = queue_frame(m, opts, mc, iter, m0, m0->frame_ready[1]);
+    if (rc) return member_failed(g, m, rc);
+  }
+  for (rm_ctx* m : g->members) {
+    RM_CUDA(g, cudaSetDevice(m->device));
+    RM_CUDA(g, cudaStreamSynchronize(m->stream));
+    if ((rc = check_watchdog(m))) return member_failed(g, m, rc);
+  }
+  return RM_OK;
+}
+
+// TonemapImage of the group's frame + read-back from member 0 (async_slot < 0: blocking)
+int tonemap(rm_ctx* g, const void* opts, size_t len, uint32_t* out, int async_slot) {
+  rm_ctx* m0 = g->members[0];
+  if (!opts || len != RM_OPTS_BYTES || !out) return fail(g, RM_ERR_INVALID_ARG, "rm_tonemap: bad opts blob or null output");
+  if (!m0->d_accum) return fail(g, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  RmOpts o;
+  decode_opts(opts, &o);
+  if (o.width != m0->W || o.height != m0->H) return fail(g, RM_ERR_BAD_OPTS, "rm_tonemap: TRenderOpts.resolution does not match the framebuffer");
+  const int b = m0->argb_cur;
+  uint32_t* frame = m0->d_argb2[b];
+  const size_t n = (size_t)m0->W * m0->H;
+  if (async_slot >= 0 && m0->copy_pending[async_slot]) {
+    RM_CUDA(g, cudaEventSynchronize(m0->copy_done[m0->slot_buffer[async_slot]]));
+    m0->copy_pending[async_slot] = false;
+  }
+  for (rm_ctx* m : g->members) {
+    RM_CUDA(g, cudaSetDevice(m->device));
+    if (!argb_is_fresh(m, frame, 0, o.gamma)) {  // not written by the render launch: tonemap the tiles this member owns
+      EventPair t = begin_timed(m, 1);
+      cudaError_t e = rm_launch_tonemap(m->d_accum, o.gamma, m->W, m->H, m->shard, frame, 2, m->stream);
+      end_timed(m, t);
+      if (e != cudaSuccess) return cuda_fail(g, e, "tonemap kernel launch");
+      m->stats.kernel_launches += 1;
+      m->argb_fresh_ptr = frame;
+      m->argb_fresh_packed = 0;
+      m->argb_fresh_gamma = o.gamma;
+    }
+    if (m != m0) {  // member 0's stream (which does the read-back) waits for every member's tiles
+      RM_CUDA(g, cudaEventRecord(m->frame_ready[0], m->stream));
+      RM_CUDA(g, cudaStreamWaitEvent(m0->stream, m->frame_ready[0], 0));
+    }
+  }
+  RM_CUDA(g, cudaSetDevice(m0->device));
+  if (async_slot < 0) {
+    EventPair t2 = begin_timed(m0, 3);
+    cudaError_t e = cudaMemcpyAsync(out, frame, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, m0->stream);
+    end_timed(m0, t2);
+    if (e != cudaSuccess) return cuda_fail(g, e, "argb read-back");
+    RM_CUDA(g, cudaStreamSynchronize(m0->stream));
+    m0->stats.d2h_bytes += n * sizeof(uint32_t);
+    for (rm_ctx* m : g->members) {
+      const int rc = check_watchdog(m);
+      if (rc) return member_failed(g, m, rc);
+    }
+    return RM_OK;
+  }
+  RM_CUDA(g, cudaEventRecord(m0->frame_ready[b], m0->stream));
+  RM_CUDA(g, cudaStreamWaitEvent(m0->copy_stream, m0->frame_ready[b], 0));
+  RM_CUDA(g, cudaMemcpyAsync(out, frame, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, m0->copy_stream));
+  RM_CUDA(g, cudaEventRecord(m0->copy_done[b], m0->copy_stream));
+  m0->copy_pending[async_slot] = true;
+  m0->slot_buffer[async_slot] = b;
+  m0->stats.d2h_bytes += n * sizeof(uint32_t);
+  // the next frame goes to the other buffer -- on every member, once the transfer that last used it has drained
+  m0->argb_cur = b ^ 1;
+  retarget(g);
+  for (int s2 = 0; s2 < 2; ++s2)
+    if (m0->copy_pending[s2] && m0->slot_buffer[s2] == m0->argb_cur)
+      for (rm_ctx* m : g->members) RM_CUDA(g, cudaStreamWaitEvent(m->stream, m0->copy_done[m0->argb_cur], 0));
+  // ... and nobody may start writing into it while another member's stores of the PREVIOUS use are in flight:
+  // those were ordered before member 0's read-back by the events above.
+  return RM_OK;
+}
+
+int wait(rm_ctx* g, int slot) {
+  const int rc = rm_wait(g->members[0], slot);
+  return rc ? member_failed(g, g->members[0], rc) : RM_OK;
+}
+
+// parity hook: every pixel is rendered by exactly one member (the others hold zeros there)
+int read_accum(rm_ctx* g, float* out) {
+  rm_ctx* m0 = g->members[0];
+  if (!out) return fail(g, RM_ERR_INVALID_ARG, "rm_read_accum: null output");
+  if (!m0->d_accum) return fail(g, RM_ERR_NO_FRAMEBUFFER, "no framebuffer (rm_clear_accum)");
+  const size_t n = (size_t)m0->W * m0->H;
+  std::vector<float> tmp(n * 4);
+  std::memset(out, 0, n * 4 * sizeof(float));
+  for (rm_ctx* m : g->members) {
+    const int rc = rm_read_accum(m, tmp.data());
+    if (rc) return member_failed(g, m, rc);
+    for (size_t i = 0; i < n; ++i)
+      if (tmp[4 * i + 3] != 0.0f) std::memcpy(out + 4 * i, tmp.data() + 4 * i, 4 * sizeof(float));
+  }
+  return RM_OK;
+}
+
+// work summed over the members; times = the slowest member (they run concurrently)
+int get_stats(rm_ctx* g, rm_stats* out) {
+  rm_stats a{};
+  for (rm_ctx* m : g->members) {
+    rm_stats s{};
+    const int rc = rm_get_stats(m, &s);
+    if (rc) return member_failed(g, m, rc);
+    a.steps += s.steps; a.taps += s.taps; a.outer_iters += s.outer_iters; a.pixel_samples += s.pixel_samples;
+    a.kernel_launches += s.kernel_launches; a.render_launches += s.render_launches;
+    a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes;
+    a.render_ms = s.render_ms > a.render_ms ? s.render_ms : a.render_ms;
+    a.tonemap_ms = s.tonemap_ms > a.tonemap_ms ? s.tonemap_ms : a.tonemap_ms;
+    a.h2d_ms = s.h2d_ms > a.h2d_ms ? s.h2d_ms : a.h2d_ms;
+    a.d2h_ms = s.d2h_ms > a.d2h_ms ? s.d2h_ms : a.d2h_ms;
+  }
+  *out = a;
+  return RM_OK;
+}
+
+}  // namespace grp

@@ -69,6 +69,16 @@ k_tonemap_packed(const float4* __restrict__ accum, float gamma, int W, int H,
   argb[slot] = id >= 0 ? tonemap_pack(accum[id], gamma) : 0u;
 }
 
+// only the pixels this shard owns, pixel-indexed: several GPUs fill ONE frame (possibly over NVLink)
+__global__ void __launch_bounds__(256)
+k_tonemap_owned(const float4* __restrict__ accum, float gamma, int W, int H,
+                const __grid_constant__ RmShard sh, uint32_t* __restrict__ argb) {
+  const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (slot >= sh.slots) return;
+  const int id = rm_slot_to_pixel(sh, slot, W, H);
+  if (id >= 0) argb[id] = tonemap_pack(accum[id], gamma);
+}
+
 __global__ void __launch_bounds__(256)
 k_pack_accum(const float4* __restrict__ accum, int W, int H, const __grid_constant__ RmShard sh,
              float4* __restrict__ packed) {
@@ -88,9 +98,7 @@ k_unpack_shards(const T* __restrict__ parts, int world, long long stride, int W,
   RmShard sh = sh0;
   sh.rank = r;
   sh.world = world;
-  const long long tiles = (long long)sh.tiles_x * sh.tiles_y;
-  sh.owned_tiles = tiles > r ? (int)((tiles - r + world - 1) / world) : 0;
-  sh.slots = (long long)sh.owned_tiles * sh.tile_w * sh.tile_h;
+  rm_shard_layout(sh, W, H);
   if (i >= sh.slots) return;
   const int id = rm_slot_to_pixel(sh, i, W, H);
   if (id >= 0) frame[id] = parts[(size_t)r * stride + i];
@@ -132,7 +140,8 @@ cudaError_t rm_launch_tonemap(const float4* d_accum, float gamma, int W, int H, 
   if (packed) {
     if (shard.slots <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((shard.slots + 255) / 256);
-    k_tonemap_packed<<<blocks, 256, 0, stream>>>(d_accum, gamma, W, H, shard, d_argb);
+    if (packed == 2) k_tonemap_owned<<<blocks, 256, 0, stream>>>(d_accum, gamma, W, H, shard, d_argb);
+    else k_tonemap_packed<<<blocks, 256, 0, stream>>>(d_accum, gamma, W, H, shard, d_argb);
   } else {
     const int n = W * H;
     k_tonemap_linear<<<(n + 255) / 256, 256, 0, stream>>>(d_accum, gamma, n, d_argb);

@@ -2,15 +2,19 @@
 #pragma once
 #include "rm_types.h"
 
-// Maps a work slot of this shard to a pixel id (or -1 for padding of edge tiles). Slots are
-// tile-major; inside a tile consecutive groups of 32 slots cover 8x4 pixel blocks so that a warp
-// traces a compact bundle of primary rays.
+// Maps a work slot of this shard to a pixel id (or -1 for padding). Slots are tile-major (the rank's
+// tiles row by row); inside a tile consecutive groups of 32 slots cover 8x4 pixel blocks so that a
+// warp traces a compact bundle of primary rays.
 __host__ __device__ inline int rm_slot_to_pixel(const RmShard& sh, long long slot, int W, int H) {
   const int tile_px = sh.tile_w * sh.tile_h;
   const long long lt = slot / tile_px;
   const int r = (int)(slot - lt * tile_px);
-  const long long t = lt * sh.world + sh.rank;
-  const int ty = (int)(t / sh.tiles_x), tx = (int)(t - (long long)ty * sh.tiles_x);
+  const int ty = (int)(lt / sh.tiles_per_rank_row), k = (int)(lt - (long long)ty * sh.tiles_per_rank_row);
+  // the rank's first column in this tile row: (tx + skew * ty) mod world == rank
+  int first = (sh.rank - (int)(((long long)sh.skew * ty) % sh.world)) % sh.world;
+  if (first < 0) first += sh.world;
+  const int tx = first + k * sh.world;
+  if (tx >= sh.tiles_x) return -1;
   const int sb = r >> 5, l = r & 31;
   const int sbw = sh.tile_w >> 3;
   const int sby = sb / sbw, sbx = sb - sby * sbw;
@@ -26,7 +30,8 @@ cudaError_t rm_launch_render_plain(const uint8_t* d_vox, const float4* d_table, 
                                    cudaStream_t stream);
 
 // TonemapImage-equivalent. packed == 0: d_argb[id] for every pixel of the frame (W*H words).
-// packed != 0: d_argb[slot] for the slots of this shard (shard.slots words, padding = 0).
+// packed == 1: d_argb[slot] for the slots of this shard (shard.slots words, padding = 0).
+// packed == 2: d_argb[id] for the pixels this shard OWNS only (several GPUs fill one frame).
 cudaError_t rm_launch_tonemap(const float4* d_accum, float gamma, int W, int H, const RmShard& shard,
                               uint32_t* d_argb, int packed, cudaStream_t stream);
 
@@ -42,7 +47,7 @@ cudaError_t rm_launch_unpack_shards(const void* d_parts, int world, long long st
 // ---- fast path (rm_accel.cu, rm_render_fast.cu) ----
 #define RM_MAX_FUSED_PASSES 32
 
-// Build the occupancy acceleration data of the resident volume for one isoVal. Synchronises the stream.
+// Build the occupancy acceleration data of the resident volume for one isoVal (asynchronous on `stream`).
 cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso, int cell_shift,
                            RmAccelStorage* st, cudaStream_t stream);
 void rm_accel_free(RmAccelStorage* st);
@@ -72,11 +77,12 @@ int rm_persist_pick_passes(int available);
 // by pixel id or, argb_packed != 0, by shard slot (padding slots = 0). d_queue: one 64-bit ticket
 // counter owned by the context, *queue_base its expected value (updated by this call; never reset).
 // block_threads: 512 / 768 / 1024 threads of the one resident block per SM (128 / 80 / 64 registers).
+// group_warps: warps that draw their bundles together and meet at a named barrier per draw (1 = free-running).
 cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
-                                     int block_threads, cudaStream_t stream);
+                                     int block_threads, int group_warps, cudaStream_t stream);
 
 // ---- warp-scheduled state machine (rm_render_warp.cu), RM_OPT_KERNEL = 2 ----
 int rm_warp_blocks_per_sm(int count);

@@ -29,14 +29,39 @@ struct RmOpts {
   RmMaterial mat[4];
 };
 
-// Interleaved tile ownership: this context renders tiles t with t % world == rank.
+// Interleaved tile ownership: the frame is cut into tile_w x tile_h pixel tiles and tile
+// (i, j) belongs to rank (i + skew * j) mod world -- diagonal stripes. (Round 1 dealt tiles row-major,
+// t mod world: with 60 or 120 tiles per row and 8 ranks that degenerates into vertical stripes, and
+// the render cost is anything but uniform across columns: 4 % load imbalance by the cost model of
+// tools/simt_model.py, 0.2 % with the skew at 16 x 8 tiles.) Every rank owns exactly tiles_per_rank_row
+// tile columns per tile row; columns beyond the frame (when tiles_x is not a multiple of world) are
+// padding, like the pixels of edge tiles beyond the frame.
 struct RmShard {
   int rank, world;
   int tile_w, tile_h;     // tile extent in pixels (multiples of 8 x 4)
   int tiles_x, tiles_y;   // tile grid over the framebuffer
-  int owned_tiles;        // tiles owned by this rank
-  long long slots;        // owned_tiles * tile_w * tile_h (includes padding of edge tiles)
+  int tiles_per_rank_row; // ceil(tiles_x / world)
+  int skew;               // coprime to world
+  int owned_tiles;        // tiles_per_rank_row * tiles_y (incl. padding tiles)
+  long long slots;        // owned_tiles * tile_w * tile_h (includes padding)
 };
+
+// Fills the derived fields of a shard for a W x H frame. Shared by the host API, the unpack kernel and
+// (restated) raymarchcl_b200/dist.py:ShardLayout.
+__host__ __device__ inline void rm_shard_layout(RmShard& s, int W, int H) {
+  s.tiles_x = W > 0 ? (W + s.tile_w - 1) / s.tile_w : 0;
+  s.tiles_y = H > 0 ? (H + s.tile_h - 1) / s.tile_h : 0;
+  s.tiles_per_rank_row = (s.tiles_x + s.world - 1) / s.world;
+  const int cand[5] = {3, 5, 7, 2, 1};
+  s.skew = 1;
+  for (int k = 0; k < 5; ++k) {
+    int a = cand[k], b = s.world;
+    while (b) { const int t = a % b; a = b; b = t; }
+    if (a == 1) { s.skew = cand[k]; break; }
+  }
+  s.owned_tiles = s.tiles_per_rank_row * s.tiles_y;
+  s.slots = (long long)s.owned_tiles * s.tile_w * s.tile_h;
+}
 
 struct RmCounters {  // reference-equivalent work, see rm_stats in raymarch_b200.h
   unsigned long long steps, taps, outer;

@@ -2,8 +2,8 @@
 
 The reference is single-device (core.clj:121-123). A work-item reads only read-only buffers and
 its own ``pixels[id]`` (renderer.cl:483-492), so the frame shards by pixels with no exchange until
-the end: every rank holds the whole volume and renders the tiles ``t % world == rank``
-(round-robin, because cost varies ~10x across the image), then the packed ARGB tiles are gathered
+the end: every rank holds the whole volume and renders the tiles ``(i + skew*j) % world == rank``
+(diagonal stripes, because cost varies ~10x across the image and is far from uniform across columns), then the packed ARGB tiles are gathered
 to rank 0 in one collective (NCCL over NVLink under torchrun; gloo in the CPU tests) and
 de-interleaved into the frame. One process per GPU; ``torch.distributed`` is plumbing only.
 
@@ -17,8 +17,20 @@ from typing import List, Optional
 import numpy as np
 
 
+def _skew(world: int) -> int:
+    """Smallest of (3, 5, 7, 2, 1) coprime to ``world`` (csrc/rm_types.h:rm_shard_layout)."""
+    from math import gcd
+    for s in (3, 5, 7, 2, 1):
+        if gcd(s, world) == 1:
+            return s
+    return 1
+
+
 @dataclass(frozen=True)
 class ShardLayout:
+    """Host mirror of ``RmShard`` / ``rm_shard_layout`` / ``rm_slot_to_pixel``: tile (i, j) belongs to rank
+    ``(i + skew*j) % world`` (diagonal stripes); every rank owns ``tiles_per_rank_row`` tile columns per
+    tile row, columns beyond the frame being padding."""
     width: int
     height: int
     world: int
@@ -37,31 +49,40 @@ class ShardLayout:
     def tiles(self) -> int:
         return self.tiles_x * self.tiles_y
 
+    @property
+    def tiles_per_rank_row(self) -> int:
+        return (self.tiles_x + self.world - 1) // self.world
+
+    @property
+    def skew(self) -> int:
+        return _skew(self.world)
+
     def owned_tiles(self, rank: int) -> int:
-        return (self.tiles - rank + self.world - 1) // self.world if self.tiles > rank else 0
+        return self.tiles_per_rank_row * self.tiles_y
 
     def slots(self, rank: int) -> int:
         return self.owned_tiles(rank) * self.tile_w * self.tile_h
 
     @property
     def max_slots(self) -> int:
-        return max(self.slots(r) for r in range(self.world))
+        return self.slots(0)
 
     def slot_pixel_index(self, rank: int) -> np.ndarray:
-        """int64[slots(rank)]: pixel id (y*W+x) of every work slot of ``rank``; -1 = edge padding."""
+        """int64[slots(rank)]: pixel id (y*W+x) of every work slot of ``rank``; -1 = padding."""
         n = self.slots(rank)
         slot = np.arange(n, dtype=np.int64)
         tile_px = self.tile_w * self.tile_h
         lt, r = slot // tile_px, slot % tile_px
-        t = lt * self.world + rank
-        ty, tx = t // self.tiles_x, t % self.tiles_x
+        ty, k = lt // self.tiles_per_rank_row, lt % self.tiles_per_rank_row
+        first = (rank - (self.skew * ty) % self.world) % self.world
+        tx = first + k * self.world
         sb, l = r >> 5, r & 31
         sbw = self.tile_w >> 3
         sby, sbx = sb // sbw, sb % sbw
         x = tx * self.tile_w + sbx * 8 + (l & 7)
         y = ty * self.tile_h + sby * 4 + (l >> 3)
         pid = y * self.width + x
-        pid[(x >= self.width) | (y >= self.height)] = -1
+        pid[(tx >= self.tiles_x) | (x >= self.width) | (y >= self.height)] = -1
         return pid
 
 

@@ -37,14 +37,21 @@ def _as_table(mc) -> np.ndarray:
 class Renderer:
     """One render context on one GPU (``rm_create`` .. ``rm_destroy``)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """``device``: one CUDA device id (``rm_create``) or a sequence of ids (``rm_create_multi``: one
+        context over several GPUs of a box, the frame assembled on the first one over NVLink)."""
         self._lib = _lib.load()
         h = C.c_void_p()
-        rc = self._lib.rm_create(int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self._lib.rm_create_multi(ids, len(device), C.byref(h))
+            self.device = int(device[0])
+        else:
+            rc = self._lib.rm_create(int(device), C.byref(h))
+            self.device = int(device)
         if rc != _lib.RM_OK:
             raise RaymarchError(rc, self._lib.rm_last_error(None).decode())
         self._h = h
-        self.device = int(device)
         self.width = self.height = 0
         self.vres = None
         self._keep: List[Any] = []
@@ -242,6 +249,14 @@ class Renderer:
     def stats(self) -> Dict[str, Any]:
         st = RmStats()
         self._check(self._lib.rm_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def member_count(self) -> int:
+        return int(self._lib.rm_member_count(self._h))
+
+    def member_stats(self, member: int) -> Dict[str, Any]:
+        st = RmStats()
+        self._check(self._lib.rm_get_member_stats(self._h, int(member), C.byref(st)))
         return st.as_dict()
 
     def reset_stats(self) -> None:
