@@ -85,9 +85,12 @@ typedef enum rm_option {
   RM_OPT_WAVE_CHUNK = 8,   /* kernel 3: (pixel, pass) items per chunk of the pipeline (1024..2^24, default 2^24) */
   RM_OPT_WAVE_REFILL = 9,  /* kernel 3: the trace kernel hands new rays to idle lanes once this many lanes of a
                               warp are idle (1 = at once ... 32 = the warp starts 32 rays together) */
-  RM_OPT_PERSIST_BLOCK = 10, /* kernel 0: threads of the one resident block per SM: 0 = default, 512, 768, 1024 */
-  RM_OPT_PERSIST_GROUP = 11  /* kernel 0: warps that draw their work bundles together and meet at a barrier per draw
-                               (1 = every warp free-running; rounded down to a divisor of the block's warps, <= 15) */
+  RM_OPT_PERSIST_BLOCK = 10, /* kernel 0: resident block layout: 0 = default, 1024 (x 1 block per SM, 64 registers)
+                               or 256 (x 5, 48 registers) threads */
+  RM_OPT_PERSIST_SMEM = 12,  /* kernel 0: 1 (default) = stage the 4-bit distance map into shared memory by bulk TMA when a
+                               copy per resident block fits the SM; 0 = always read the byte map from global memory */
+  RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 1 (default) = every warp draws its next work bundle on its own;
+                               > 1 = the warps of a block draw together and meet at the block barrier per draw */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */

@@ -77,6 +77,7 @@ struct rm_ctx {
   unsigned long long* d_queue = nullptr;  // [0] work queue head of the warp kernel, [1] bundle tickets of the default kernel
   unsigned long long queue_base = 0;      // expected value of d_queue[1] (monotonic, rm_launch_render_persist)
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
+  int persist_smem = 1;                   // stage the 4-bit distance map into shared memory when it fits (RM_OPT_PERSIST_SMEM)
   int persist_group = 1;                  // warps of the default kernel that draw bundles together (RM_OPT_PERSIST_GROUP)
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
@@ -383,7 +384,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
           int packed = 0;
           uint32_t* argb = fused_argb_target(c, &packed);
           e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
-                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, c->persist_block, c->persist_group, c->stream);
+                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, c->persist_block, c->persist_group, c->persist_smem, c->stream);
           launched = 1;
           if (e == cudaSuccess && argb) {
             c->argb_fresh_ptr = argb;
@@ -1142,9 +1143,12 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
       c->trip_limit = (unsigned)value;
       return RM_OK;
     case RM_OPT_PERSIST_BLOCK:
-      if (value != 0 && value != 512 && value != 768 && value != 1024)
-        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 512, 768 or 1024 threads");
+      if (value != 0 && value != 256 && value != 1024)
+        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 1024 (x 1 block per SM) or 256 (x 5) threads");
       c->persist_block = (int)value;
+      return RM_OK;
+    case RM_OPT_PERSIST_SMEM:
+      c->persist_smem = value != 0;
       return RM_OK;
     case RM_OPT_PERSIST_GROUP:
       if (value < 1 || value > 32) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_GROUP: 1..32 warps");

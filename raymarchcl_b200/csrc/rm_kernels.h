@@ -76,13 +76,14 @@ int rm_persist_pick_passes(int available);
 // kernel. d_argb (optional): the ARGB words of the frame so far (TonemapImage with opts.gamma), indexed
 // by pixel id or, argb_packed != 0, by shard slot (padding slots = 0). d_queue: one 64-bit ticket
 // counter owned by the context, *queue_base its expected value (updated by this call; never reset).
-// block_threads: 512 / 768 / 1024 threads of the one resident block per SM (128 / 80 / 64 registers).
-// group_warps: warps that draw their bundles together and meet at a named barrier per draw (1 = free-running).
+// block_threads: layout of the resident blocks: 1024 (x 1 per SM, 64 registers) or 256 (x 5 per SM, 48 registers).
+// smem_map: 0 = read the distance map from global memory even when the 4-bit copy would fit the SM's shared memory.
+// group_warps: > 1 = the warps of a block draw their bundles together and meet at the block barrier per draw (1 = free-running).
 cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
-                                     int block_threads, int group_warps, cudaStream_t stream);
+                                     int block_threads, int group_warps, int smem_map, cudaStream_t stream);
 
 // ---- warp-scheduled state machine (rm_render_warp.cu), RM_OPT_KERNEL = 2 ----
 int rm_warp_blocks_per_sm(int count);

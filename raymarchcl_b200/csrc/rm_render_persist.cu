@@ -61,13 +61,15 @@ __device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
   return 0xff000000u | (ch[0] << 16) | (ch[1] << 8) | ch[2];
 }
 
-// kThreads: threads of the one resident block per SM = 65536 / registers per thread. 1024 (64
-// registers, some spills in the shading code), 768 (80) and 512 (128, no spills) are compiled;
-// RM_OPT_PERSIST_BLOCK selects, the default is the measured best.
-template <bool kCount, bool kNib, int kThreads>
-__global__ void __launch_bounds__(kThreads, 1)
+// Layouts (threads per block x resident blocks per SM), RM_OPT_PERSIST_BLOCK: 1024 x 1 (64 registers,
+// 32 warps per SM, room for a 200 KB distance map) and 256 x 5 (48 registers, 40 warps, <= 40 KB map per
+// block). Every block stages its own copy of the map, so the 128 KiB map of a 256^3 volume only fits
+// the first layout. (640 x 2 at 48 registers was measured too: like 1024 x 1.)
+template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ PersistParams P) {
   const RmOpts& o = fused::g_opts;
+  constexpr bool kNib = (kMap & fused::kMapNib) != 0;
   if (kNib) {
     // Stage the distance map: bulk async copies (TMA engine, no registers, no per-thread loads)
     // complete on an mbarrier that every thread of the block then waits on.
@@ -105,35 +107,36 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
   s.time = P.times[lane_used ? pass : 0];
 
   // Scheduling granularity. group_warps == 1: every warp draws its next bundle on its own (no warp ever
-  // waits for another). group_warps == G > 1: G neighbouring warps draw G consecutive bundles together and
-  // meet at a named barrier before the next draw -- they then run the same phases of the routine at the
-  // same time and share the instruction cache lines they pull in (the kernel's code is twice the 32 KB
-  // L1.5 instruction cache; ncu: stall_no_instruction 2.3 per issue with free-running warps).
-  __shared__ unsigned long long s_ticket[32][2];
-  const int G = P.group_warps;
+  // waits for another). group_warps == warps of the block: the block draws that many consecutive bundles
+  // together and meets at the block barrier before the next draw, like a non-persistent block of the
+  // per-item kernel -- its warps then run the same phases of the routine at the same time and share the
+  // instruction cache lines they pull in. (Groups smaller than the block were measured too, over named
+  // barriers: no better, and a dynamic barrier id makes ptxas reserve all 16 barriers, which caps the
+  // 256-thread layout at 4 resident blocks.)
+  __shared__ unsigned long long s_ticket[2];
+  const bool grouped = P.group_warps > 1;
   const int warp = (int)(threadIdx.x >> 5);
-  const int group = warp / G, warp_in_group = warp - group * G;
   unsigned round = 0;
   for (;;) {
     unsigned long long t = 0;
-    if (G == 1) {
+    if (!grouped) {
       if (lane == 0) t = atomicAdd(P.queue, 1ull) - P.queue_base;
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= (unsigned long long)P.bundles) break;
     } else {
-      if (warp_in_group == 0 && lane == 0) s_ticket[group][round & 1u] = atomicAdd(P.queue, (unsigned long long)G) - P.queue_base;
-      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G * 32) : "memory");
-      const unsigned long long t0 = s_ticket[group][round & 1u];
+      if (threadIdx.x == 0) s_ticket[round & 1u] = atomicAdd(P.queue, (unsigned long long)(kThreads / 32)) - P.queue_base;
+      __syncthreads();
+      const unsigned long long t0 = s_ticket[round & 1u];
       ++round;
-      if (t0 >= (unsigned long long)P.bundles) break;  // the whole group leaves together
-      t = t0 + (unsigned)warp_in_group;
+      if (t0 >= (unsigned long long)P.bundles) break;  // the whole block leaves together
+      t = t0 + (unsigned)warp;
       if (t >= (unsigned long long)P.bundles) continue;  // ragged last draw: sit this round out
     }
     const long long slot = (long long)t * P.ppb + sub;
     const bool in_shard = lane_used && slot < sh.slots;
     const int id = in_shard ? rm_slot_to_pixel(sh, slot, o.width, o.height) : -1;
     float3 c = f3s(0.0f);
-    if (id >= 0) c = fused::render_pixel_sample<kCount, kNib>(cnt, s, id);
+    if (id >= 0) c = fused::render_pixel_sample<kCount, kMap>(cnt, s, id);
     __syncwarp();
     // pixels = mix(pixels, colour_k, frameBlend_k), k = 0 .. m-1 in pass order (renderer.cl:492)
     float3 p = f3s(0.0f);
@@ -173,26 +176,25 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
 // function attributes are per device: set once per (device, instantiation)
 std::once_flag g_attr_once[64][16];
 
-template <bool kCount, bool kNib, int kThreads>
+template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 cudaError_t launch(const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev, cudaStream_t stream) {
   cudaError_t attr = cudaSuccess;
-  constexpr int variant = ((kThreads / 256 - 1) << 2) | (kCount ? 2 : 0) | (kNib ? 1 : 0);
+  constexpr int variant = ((kThreads == 1024 ? 0 : 1) << 3) | (kCount ? 4 : 0) | kMap;
   std::call_once(g_attr_once[dev & 63][variant], [&] {
-    if (kNib) attr = cudaFuncSetAttribute(k_render_persist<kCount, kNib, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PERSIST_MAX_SMEM);
-    else attr = cudaFuncSetAttribute(k_render_persist<kCount, kNib, kThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    if (kMap & fused::kMapNib) attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PERSIST_MAX_SMEM / kBlocksPerSM);
+    else attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   });
   if (attr != cudaSuccess) return attr;
-  k_render_persist<kCount, kNib, kThreads><<<blocks, kThreads, smem, stream>>>(shard, P);
+  k_render_persist<kCount, kMap, kThreads, kBlocksPerSM><<<blocks, kThreads, smem, stream>>>(shard, P);
   return cudaGetLastError();
 }
 
-template <bool kNib>
+template <int kMap>
 cudaError_t launch_any(bool count, int threads, const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev,
                        cudaStream_t stream) {
-  if (count) return launch<true, kNib, 1024>(shard, P, blocks, smem, dev, stream);
-  if (threads == 512) return launch<false, kNib, 512>(shard, P, blocks, smem, dev, stream);
-  if (threads == 768) return launch<false, kNib, 768>(shard, P, blocks, smem, dev, stream);
-  return launch<false, kNib, 1024>(shard, P, blocks, smem, dev, stream);
+  if (count) return launch<true, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
+  if (threads == 256) return launch<false, kMap, 256, 5>(shard, P, blocks, smem, dev, stream);
+  return launch<false, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
 }
 
 }  // namespace
@@ -210,7 +212,7 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
-                                     int block_threads, int group_warps, cudaStream_t stream) {
+                                     int block_threads, int group_warps, int smem_map, cudaStream_t stream) {
   if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
   if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
   PersistParams P;
@@ -231,14 +233,14 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
   P.nib = accel.nib;
   P.nib_bytes = accel.nib_bytes;
-  const bool use_nib = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= RM_PERSIST_MAX_SMEM;
-  const int threads = d_counters ? 1024 : (block_threads == 512 || block_threads == 768 ? block_threads : 1024);
+  const int threads = d_counters ? 1024 : (block_threads == 256 ? 256 : 1024);
+  const int blocks_per_sm = threads == 1024 ? 1 : 5;
+  const bool use_nib = smem_map != 0 && accel.nib != nullptr && accel.nib_bytes > 0 &&
+                       accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
   const int warps_per_block = threads / 32;
   long long blocks = (P.bundles + warps_per_block - 1) / warps_per_block;
-  if (blocks > num_sms) blocks = num_sms;
-  // whole groups per block, at most 15 of them (named barriers 1..15): round the request up to the next fit
-  int G = group_warps < 1 ? 1 : (group_warps > warps_per_block ? warps_per_block : group_warps);
-  while (G > 1 && G < warps_per_block && (warps_per_block % G != 0 || warps_per_block / G > 15)) ++G;
+  if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;
+  const int G = group_warps > 1 ? warps_per_block : 1;  // block-synchronous draws, or free-running warps
   P.group_warps = G;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -246,8 +248,14 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   if ((e = cudaMemcpyToSymbolAsync(fused::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbolAsync(fused::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
   const size_t smem = use_nib ? accel.nib_bytes : 0;
-  e = use_nib ? launch_any<true>(d_counters != nullptr, threads, shard, P, (int)blocks, smem, dev, stream)
-              : launch_any<false>(d_counters != nullptr, threads, shard, P, (int)blocks, smem, dev, stream);
+  const int map = (use_nib ? fused::kMapNib : 0) | (accel.cell_shift == 2 ? fused::kMapCell4 : 0);
+  const bool cnt = d_counters != nullptr;
+  switch (map) {
+    case 0: e = launch_any<0>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    case 1: e = launch_any<1>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    case 2: e = launch_any<2>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    default: e = launch_any<3>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+  }
   if (e != cudaSuccess) return e;
   // Every warp (group of G warps) of the grid draws tickets, G at a time, until it draws one past the end:
   // ceil(bundles / G) successful draws plus exactly one failing draw per group.

@@ -12,7 +12,7 @@
 //     thread, ~10 % of the executed instructions and 8.5 GB of DRAM write-backs per C2 frame;
 //   * the distance map is read from SHARED MEMORY: 4 bits per macro-cell (Chebyshev distance
 //     saturated at 15), staged once per resident block with a bulk TMA copy (cp.async.bulk +
-//     mbarrier, rm_render_persist.cu). At <= 64^3 cells that is <= 128 KiB. kNib == false reads the
+//     mbarrier, rm_render_persist.cu). At <= 64^3 cells that is <= 128 KiB. without kMapNib the routine reads the
 //     byte map from global memory instead (grids whose map does not fit the SM).
 //
 // tests/hostsim compiles this header for the host (RM_NIB_BASE is then a plain pointer) and compares
@@ -46,9 +46,24 @@ static __constant__ RmAccel g_accel;
 #if defined(__CUDACC__)
 extern __shared__ __align__(16) uint8_t rm_smem_nib[];  // the 4-bit distance map of this block
 #define RM_NIB_BASE rm_smem_nib
+// The map's address in the shared window, computed once per march and kept in a register (the empty asm
+// makes it opaque: otherwise the compiler re-derives it from SR_CgaCtaId inside the loop, 4 instructions
+// per lookup), and a plain ld.shared through it.
+RM_DEV unsigned nib_base() {
+  unsigned a = (unsigned)__cvta_generic_to_shared(rm_smem_nib);
+  asm("" : "+r"(a));
+  return a;
+}
+RM_DEV unsigned nib_load(unsigned base, unsigned byte) {
+  unsigned v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + byte));
+  return v;
+}
 #else
 static const uint8_t* rm_host_nib = nullptr;  // host simulation: the same packed map in host memory
 #define RM_NIB_BASE rm_host_nib
+inline unsigned nib_base() { return 0u; }
+inline unsigned nib_load(unsigned, unsigned byte) { return rm_host_nib[byte]; }
 #endif
 
 // Reference-equivalent work counters: a real object (by reference) in the counting kernels, an
@@ -110,13 +125,18 @@ RM_DEV int occ_at(int x, int y, int z) {
 RM_DEV int voxel_value(int x, int y, int z) {
   return __ldg(g_accel.vox + ((size_t)z * g_opts.rxy + (size_t)y * g_opts.rx + x));
 }
+// How the distance map is read (template parameter kMap of everything below, a bit set):
+//   kMapNib    the 4-bit copy in shared memory (else the byte map in global memory)
+//   kMapCell4  the macro-cell is one 4x4x4 brick (cell_shift == 2: every volume up to 256^3), so the cell
+//              index is the brick index and the shift is an immediate
+enum { kMapNib = 1, kMapCell4 = 2 };
 // Chebyshev distance (in macro-cells, saturated) from the cell of voxel (x, y, z) to the nearest cell
-// that holds a solid voxel. kNib: the 4-bit copy in shared memory; else the byte map in global memory.
-template <bool kNib>
+// that holds a solid voxel.
+template <int kMap>
 RM_DEV int cell_dist(int x, int y, int z) {
   const int cs = g_accel.cell_shift;
   const unsigned c = (unsigned)(((z >> cs) * g_accel.my + (y >> cs)) * g_accel.mx + (x >> cs));
-  if (kNib) return (RM_NIB_BASE[c >> 1] >> ((c & 1u) << 2)) & 15;
+  if (kMap & kMapNib) return (RM_NIB_BASE[c >> 1] >> ((c & 1u) << 2)) & 15;
   return __ldg(g_accel.dist + c);
 }
 
@@ -157,14 +177,14 @@ RM_DEV unsigned taps_of_hit(int x, int y, int z, bool smooth) {
 
 // ---- the fixed-step march (renderer.cl:219-234) ----------------------------------------------------
 // Counting form: visits every sample the reference fetches (exact step counter).
-template <bool kNib>
+template <int kMap>
 RM_DEV bool march_counting(Cnt<true>& c, float3& p, float3 delta, int rem, float invS) {
   const float rxf = (float)g_opts.rx, ryf = (float)g_opts.ry, rzf = (float)g_opts.rz;
   while (rem > 0) {
     const int x = f2i_sat(p.x * rxf), y = f2i_sat(p.y * ryf), z = f2i_sat(p.z * rzf);
     c.steps++;
     if (!in_grid(x, y, z)) return false;
-    const int d = cell_dist<kNib>(x, y, z);
+    const int d = cell_dist<kMap>(x, y, z);
     if (d != 0) {
       const float reach = (float)(d - 1) * g_accel.cellf - 0.25f;
       int n = reach > 0.0f ? 1 + f2i_sat(fminf(reach * invS, 1e6f)) : 1;
@@ -188,36 +208,56 @@ RM_DEV bool march_counting(Cnt<true>& c, float3& p, float3 delta, int rem, float
 
 // Production form (see march_fast in rm_scene_plain.cuh for the derivation of the skip length and
 // of the XU-free conversions): samples known to be empty cost three adds each and no fetch.
-template <bool kNib>
+//
+// This loop is more than half of the kernel's executed instructions, at ~10 active lanes: every lane
+// of a warp pays for the union of the paths any lane takes, so it is written to have few of them.
+//   * the skip length is computed without a branch for every d: (float)(d-1) = as_float(2^23 + d) -
+//     (2^23 + 1), and k = rint((d-1)*A - B) clamps to 0 for d <= 1;
+//   * the skipped adds run in a 2x-unrolled loop (+1 predicated add): 14 instructions of code instead
+//     of the 60 of an 8/4/2/1 ladder, and 6 executed instructions instead of ~27 for the most common
+//     skip (none: 53 % of all lookups sit in or next to an occupied cell);
+//   * with 4-voxel cells the cell index IS the brick index.
+// Which samples are looked at only decides how many fetches are saved, never the result: a hit is
+// always decided by the solid bit of the exact voxel of a sample of the fp32 recurrence.
+template <int kMap>
 RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
   RM_STAT_MARCH();
   const float A = g_accel.cellf * invS, B = 0.25f * invS + 0.5f;  // invS <= 2000 (march_delta)
+  float px = p.x, py = p.y, pz = p.z;
+  bool found = false;
+  const unsigned nib = (kMap & kMapNib) ? nib_base() : 0u;
+  const float rxf = g_accel.rxf, ryf = g_accel.ryf, rzf = g_accel.rzf;
+  const unsigned rx = g_opts.rx, ry = g_opts.ry, rz = g_opts.rz;
+  const int cs = (kMap & kMapCell4) ? 2 : g_accel.cell_shift, my = g_accel.my, mx = g_accel.mx;
   while (rem > 0) {
-    const int x = f2i_sat(p.x * g_accel.rxf), y = f2i_sat(p.y * g_accel.ryf), z = f2i_sat(p.z * g_accel.rzf);
-    if (!in_grid(x, y, z)) return false;
-    const int d = cell_dist<kNib>(x, y, z);
+    const int x = f2i_sat(px * rxf), y = f2i_sat(py * ryf), z = f2i_sat(pz * rzf);
+    if ((unsigned)x >= rx || (unsigned)y >= ry || (unsigned)z >= rz) break;
+    const unsigned c = (unsigned)(((z >> cs) * my + (y >> cs)) * mx + (x >> cs));
+    int d;
+    if (kMap & kMapNib) d = (nib_load(nib, c >> 1) >> ((c & 1u) << 2)) & 15;
+    else d = __ldg(g_accel.dist + c);
     RM_STAT_LOOKUP();
     RM_STAT_EVENT(d == 0 ? 13 : (d == 1 ? 14 : (d == 2 ? 15 : 16)));
-    int n = 1;  // samples consumed by this iteration: this one plus the ones known to be empty
-    if (d > 1) {
-      const float dm1 = __int_as_float(0x4b000000 | (d - 1)) - 8388608.0f;
-      const float k = (dm1 * A - B) + 12582912.0f;
-      n = 1 + (__float_as_int(k) - 0x4b400000);
-    } else if (d == 0 && solid_at(x, y, z)) {
-      return true;
+    if (d == 0) {
+      const unsigned bi = (kMap & kMapCell4) ? c : (unsigned)(((z >> 2) * g_accel.by + (y >> 2)) * g_accel.bx + (x >> 2));
+      if ((unsigned)(__ldg(g_accel.solid + bi) >> brick_bit(x, y, z)) & 1u) { found = true; break; }
     }
-    if (n >= rem) return false;  // the march runs out inside space known to be empty: a miss
+    // samples consumed by this iteration: this one plus the ones known to be empty
+    const float dm1 = __int_as_float(0x4b000000 + d) - 8388609.0f;
+    const int k = __float_as_int((dm1 * A - B) + 12582912.0f) - 0x4b400000;
+    const int n = 1 + (k > 0 ? k : 0);
+    if (n >= rem) break;  // the march runs out inside space known to be empty: a miss
     rem -= n;
     RM_STAT_SKIP(n);
-    for (; n >= 8; n -= 8) {
-      p = p + delta; p = p + delta; p = p + delta; p = p + delta;
-      p = p + delta; p = p + delta; p = p + delta; p = p + delta;
+#pragma unroll 1
+    for (int h = n >> 1; h > 0; --h) {
+      px += delta.x; py += delta.y; pz += delta.z;
+      px += delta.x; py += delta.y; pz += delta.z;
     }
-    if (n & 4) { p = p + delta; p = p + delta; p = p + delta; p = p + delta; }
-    if (n & 2) { p = p + delta; p = p + delta; }
-    if (n & 1) p = p + delta;
+    if (n & 1) { px += delta.x; py += delta.y; pz += delta.z; }
   }
-  return false;
+  p = f3(px, py, pz);
+  return found;
 }
 
 // renderer.cl:209-237 without the normal; g = rpos.y + groundY is passed in by the caller (it has it).
@@ -225,7 +265,7 @@ RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
 #ifndef RM_FUSED_SD_ATTR
 #define RM_FUSED_SD_ATTR __device__ __noinline__
 #endif
-template <bool kCount, bool kNib>
+template <bool kCount, int kMap>
 RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 delta, int steps, float invS, float g,
                                     bool smooth) {
   const RmOpts& o = g_opts;
@@ -233,7 +273,7 @@ RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 de
   r.dist = g < 1e5f ? g : 1e5f;
   r.hit = false;
   r.closer = false;
-  r.p = f3s(0.0f);
+  r.p = rpos;  // (only read after a hit)
   const bool inside = rpos.x > o.boundsMin.x && rpos.x < o.boundsMax.x && rpos.y > o.boundsMin.y &&
                       rpos.y < o.boundsMax.y && rpos.z > o.boundsMin.z && rpos.z < o.boundsMax.z;
   const bool away = (rpos.x > o.boundsMax.x && dir.x > 0.0f) || (rpos.x < o.boundsMin.x && dir.x < 0.0f) ||
@@ -248,12 +288,12 @@ RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 de
     if (idist > 0.0f) p = dir * idist + p;
     p = p * o.invVoxelScale;
     bool found;
-    if constexpr (kCount) found = march_counting<kNib>(c, p, delta, steps, invS);
-    else found = march_fast<kNib>(p, delta, steps, invS);
+    if constexpr (kCount) found = march_counting<kMap>(c, p, delta, steps, invS);
+    else found = march_fast<kMap>(p, delta, steps, invS);
+    r.p = p;
     if (found) {
       RM_STAT_EVENT(5);
       r.hit = true;
-      r.p = p;
       if constexpr (kCount) {
         const int x = f2i_sat(p.x * (float)o.rx), y = f2i_sat(p.y * (float)o.ry), z = f2i_sat(p.z * (float)o.rz);
         c.taps += taps_of_hit(x, y, z, smooth);
@@ -310,7 +350,7 @@ RM_DEV void march_window(float3 ro, float3 rd, float maxDist, float& tin, float&
 #ifndef RM_FUSED_ST_ATTR
 #define RM_FUSED_ST_ATTR __device__ __noinline__
 #endif
-template <bool kCount, bool kNib>
+template <bool kCount, int kMap>
 RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist, int maxSteps, bool smooth,
                                    bool wantSurface) {
   const RmOpts& o = g_opts;
@@ -354,14 +394,14 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
         cut = k < (float)(limit - 2);
         if (cut) limit = f2i_sat(k) + 2;
       }
-      j = scene_distance<kCount, kNib>(c, pos, rd, delta, limit, invS, g, smooth);
+      j = scene_distance<kCount, kMap>(c, pos, rd, delta, limit, invS, g, smooth);
     }
     if (fabsf(j.dist) <= o.eps || dist >= maxDist) break;
     dist += j.dist;
   }
   if (!kCount && wantSurface && cut && !j.hit) {
     RM_STAT_EVENT(10);
-    j = scene_distance<kCount, kNib>(c, pos, rd, delta, o.maxVoxelIter, invS, jg, smooth);
+    j = scene_distance<kCount, kMap>(c, pos, rd, delta, o.maxVoxelIter, invS, jg, smooth);
   }
   const bool miss = dist >= maxDist;
   if (miss) {
@@ -433,7 +473,7 @@ RM_DEV float blinn_phong(float smooth, float3 rd, float3 ldir, float3 n) {
 }
 
 // renderer.cl:327-346
-template <bool kCount, bool kNib>
+template <bool kCount, int kMap>
 RM_DEV float ambient_occlusion(RM_CNT c, Lane s, float3 pos, float3 n0) {
   const RmOpts& o = g_opts;
   float ao = 1.0f, d = 0.0f;
@@ -461,7 +501,7 @@ RM_DEV float ambient_occlusion(RM_CNT c, Lane s, float3 pos, float3 n0) {
       }
       RM_STAT_EVENT(11);
       RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16 + 8 + i);
-      hdist = scene_distance<kCount, kNib>(c, q, n, delta, limit, invS, g, false).dist;
+      hdist = scene_distance<kCount, kMap>(c, q, n, delta, limit, invS, g, false).dist;
     }
     ao *= 1.0f - cl_max((d - hdist) * o.aoAmp / d, 0.0f);
   }
@@ -472,12 +512,12 @@ RM_DEV float ambient_occlusion(RM_CNT c, Lane s, float3 pos, float3 n0) {
 #ifndef RM_FUSED_OL_ATTR
 #define RM_FUSED_OL_ATTR __device__ __noinline__
 #endif
-template <bool kCount, bool kNib>
+template <bool kCount, int kMap>
 RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float px, float py, float3 rd, float3 ipos, int mat, float3 n,
                                         float3 reflectCol) {
   const RmOpts& o = g_opts;
   const RmMaterial& m = o.mat[mat];
-  const float ao = ambient_occlusion<kCount, kNib>(c, s, ipos, n);
+  const float ao = ambient_occlusion<kCount, kMap>(c, s, ipos, n);
   float3 diff = sky(n) * ao;
   float3 spec = reflectCol * ao;
   float3 fin = f3s(0.0f);
@@ -495,7 +535,7 @@ RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float px, float py, fl
       const bool irrelevant = !kCount && kd == 0.0f && ks == 0.0f && zero.x == 0.0f && zero.y == 0.0f && zero.z == 0.0f;
       if (!irrelevant) {
         RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16 + 1 + i);
-        const Isec sh = sphere_trace<kCount, kNib>(c, ipos + ldir * o.shadowBias, ldir, lmax, o.shadowIter, false, false);
+        const Isec sh = sphere_trace<kCount, kMap>(c, ipos + ldir * o.shadowBias, ldir, lmax, o.shadowIter, false, false);
         const float sf = sh.distance < lmax ? 0.0f : 1.0f;
         if (sf > 0.0f) {
           diff = diff + inc * kd;
@@ -512,12 +552,12 @@ RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float px, float py, fl
 RM_DEV int mat_index(int id) { return id < 0 ? 0 : (id > 3 ? 3 : id); }
 
 // renderer.cl:407-446 with basicSceneColor (:383-405) in its bounce loop
-template <bool kCount, bool kNib>
+template <bool kCount, int kMap>
 RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal, float3 ro, float3 rd) {
   const RmOpts& o = g_opts;
   RM_STAT_LEVEL(0);
   RM_STAT_SITE(0);
-  const Isec isec = sphere_trace<kCount, kNib>(c, ro, rd, o.maxDist, o.maxIter, true, true);
+  const Isec isec = sphere_trace<kCount, kMap>(c, ro, rd, o.maxDist, o.maxIter, true, true);
   float3 col;
   if (isec.distance >= o.maxDist) {
     col = sky(rd);
@@ -533,10 +573,10 @@ RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal,
         const float3 bo = bpos + bd * 0.0075f;
         RM_STAT_LEVEL(i + 1);
         RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16);
-        const Isec ri = sphere_trace<kCount, kNib>(c, bo, bd, o.maxDist, o.maxIter, false, true);
+        const Isec ri = sphere_trace<kCount, kMap>(c, bo, bd, o.maxDist, o.maxIter, false, true);
         float3 bc;
         if (ri.objectID < 0) bc = sky(bd);
-        else bc = object_lighting<kCount, kNib>(c, s, px, py, bd, ri.pos, mat_index(ri.objectID), ri.normal,
+        else bc = object_lighting<kCount, kMap>(c, s, px, py, bd, ri.pos, mat_index(ri.objectID), ri.normal,
                                                 sky(reflect3(bd, ri.normal)));
         reflectCol = reflectCol + atmosphere(s, px, py, bo, bd, ri.distance, bc);
         if (ri.objectID < 0) break;
@@ -548,14 +588,14 @@ RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal,
       reflectCol = sky(reflect3(rd, n));
     }
     RM_STAT_LEVEL(0);
-    col = object_lighting<kCount, kNib>(c, s, px, py, rd, isec.pos, mi, n, reflectCol);
+    col = object_lighting<kCount, kMap>(c, s, px, py, rd, isec.pos, mi, n, reflectCol);
   }
   return atmosphere(s, px, py, ro, rd, isec.distance, col);
 }
 
 // One work-item of RenderImage (renderer.cl:478-494; initRenderState :467-476, cameraRayLookat
 // :456-465): returns sceneColor * exposure.
-template <bool kCount, bool kNib>
+template <bool kCount, int kMap>
 RM_DEV float3 render_pixel_sample(RM_CNT c, Lane s, int id) {
   const RmOpts& o = g_opts;
   const float4 a = table_at(s, (uint32_t)(id * 17) + f2u_wrap(s.time * 3141.3862f));
@@ -569,7 +609,7 @@ RM_DEV float3 render_pixel_sample(RM_CNT c, Lane s, int id) {
   float vy = py / (float)o.height * o.fov - o.fov * 0.5f;
   vy = vy * -o.invAspect;
   const float3 rd = unit3(right * vx + cross3(right, fwd) * vy + fwd);
-  return scene_color<kCount, kNib>(c, s, px, py, mcNormal, eye, rd) * o.exposure;
+  return scene_color<kCount, kMap>(c, s, px, py, mcNormal, eye, rd) * o.exposure;
 }
 
 }  // namespace fused

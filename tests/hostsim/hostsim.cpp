@@ -200,10 +200,14 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
       if (mode == 0) c = plain::render_pixel_sample<false>(s, plain::BrickVolume{}, id);
       else if (mode == 1) c = plain::render_pixel_sample<true>(s, plain::BrickVolume{}, id);
       else if (mode == 2) c = plain::render_pixel_sample<true>(s, plain::ByteVolume{vox}, id);
-      else if (mode == 3) c = fused::render_pixel_sample<false, true>(fused::Cnt<false>{}, lane, id);
-      else if (mode == 4) c = fused::render_pixel_sample<true, true>(fc, lane, id);
-      else if (mode == 5) c = fused::render_pixel_sample<false, false>(fused::Cnt<false>{}, lane, id);
-      else c = fused::render_pixel_sample<true, false>(fc, lane, id);
+      else if (mode == 3 && cell_shift == 2) c = fused::render_pixel_sample<false, 3>(fused::Cnt<false>{}, lane, id);
+      else if (mode == 3) c = fused::render_pixel_sample<false, 1>(fused::Cnt<false>{}, lane, id);
+      else if (mode == 4 && cell_shift == 2) c = fused::render_pixel_sample<true, 3>(fc, lane, id);
+      else if (mode == 4) c = fused::render_pixel_sample<true, 1>(fc, lane, id);
+      else if (mode == 5 && cell_shift == 2) c = fused::render_pixel_sample<false, 2>(fused::Cnt<false>{}, lane, id);
+      else if (mode == 5) c = fused::render_pixel_sample<false, 0>(fused::Cnt<false>{}, lane, id);
+      else if (cell_shift == 2) c = fused::render_pixel_sample<true, 2>(fc, lane, id);
+      else c = fused::render_pixel_sample<true, 0>(fc, lane, id);
       if (mode == 4 || mode == 6) { s.w.steps = fc.steps; s.w.taps = fc.taps; s.w.outer = fc.outer; }
       float* px = pixels + 4 * (size_t)id;
       const float3 m = lerp3(make_float3(px[0], px[1], px[2]), c, o.frameBlend);  // mix(), renderer.cl:492

@@ -121,20 +121,25 @@ def test_ragged_grid_render(gpu_renderer, oracle):
 def test_default_kernel_equals_round1_kernel_bit_for_bit(gpu_renderer):
     """Persistent warps + shared-memory distance map + in-warp blend + folded tonemap change where the
     work runs, not one bit of the result: kernel 0 == kernel 4 (per-item kernel + blend kernel +
-    tonemap kernel) on the accumulator and on the ARGB words; all three block sizes of kernel 0 too."""
+    tonemap kernel) on the accumulator and on the ARGB words; for every block layout, grouped draws and
+    with the distance map in shared or in global memory."""
     kw = dict(vres=128, width=200, height=120, iters=16, mat="metal2", dof=0.025)
     vol, opts, mcs = build_scene(**kw)
     gpu_renderer.set_option(2, 4)
     ref, argb_ref, _ = render_gpu(gpu_renderer, vol, opts, mcs, 200, 120, count=False)
     gpu_renderer.set_option(2, 0)
     try:
-        for block in (512, 768, 1024, 0):
+        for block, group, smem in ((1024, 1, 1), (1024, 1, 0), (256, 1, 1), (1024, 8, 1), (256, 1, 0), (256, 8, 0), (0, 1, 1)):
             gpu_renderer.set_option(10, block)
+            gpu_renderer.set_option(11, group)
+            gpu_renderer.set_option(12, smem)
             px, argb, _ = render_gpu(gpu_renderer, vol, opts, mcs, 200, 120, count=False)
-            assert np.array_equal(px.view(np.uint32), ref.view(np.uint32)), block
-            assert np.array_equal(argb, argb_ref), block
+            assert np.array_equal(px.view(np.uint32), ref.view(np.uint32)), (block, group, smem)
+            assert np.array_equal(argb, argb_ref), (block, group, smem)
     finally:
         gpu_renderer.set_option(10, 0)
+        gpu_renderer.set_option(11, 1)
+        gpu_renderer.set_option(12, 1)
 
 
 def test_map_too_large_for_shared_memory_uses_the_global_map(gpu_renderer, oracle):

@@ -1,0 +1,25 @@
+#!/bin/bash
+# A/B of the default kernel's block layouts / shared-memory map on C2 + ncu captures of two of them.
+set -u
+mkdir -p gpurun_out
+TAG=${1:-r02ab3}
+cp raymarchcl_b200/libraymarch_b200.so gpurun_out/${TAG}_lib.so   # the binary the captures belong to (source-line join)
+run() {
+  local name=$1; shift
+  timeout 300 python bench.py --steps ${STEPS:-8} --warmup 3 --no-e2e --no-cpu-baseline --no-parity "$@" \
+    > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+  echo "$name: $(python -c "import json;d=json.load(open('gpurun_out/${TAG}_${name}.json'));print(round(d['ms_per_step'],3), round(d['roofline']['kernel_ms_per_frame'],3))" 2>&1 | tail -1)"
+}
+run bricks --kernel bricks
+run b1024_smem --opt 10=1024 --opt 12=1
+run b1024_glob --opt 10=1024 --opt 12=0
+run b256_glob --opt 10=256 --opt 12=0
+run b256_g8 --opt 10=256 --opt 12=0 --opt 11=8
+run b1024_g32 --opt 10=1024 --opt 12=1 --opt 11=32
+for V in ${NCU_VARIANTS:-"1024,1 256,0"}; do
+  B=${V%,*}; S=${V#*,}
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_persist -s 1 -c 1 -f \
+    -o gpurun_out/${TAG}_persist_b${B}_c2 python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity \
+    --opt 10=$B --opt 12=$S > gpurun_out/${TAG}_ncu_b$B.log 2>&1
+  echo "ncu b$B rc=$?"
+done
