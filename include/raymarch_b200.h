@@ -89,8 +89,8 @@ typedef enum rm_option {
                                or 256 (x 5, 48 registers) threads */
   RM_OPT_PERSIST_SMEM = 12,  /* kernel 0: 1 (default) = stage the 4-bit distance map into shared memory by bulk TMA when a
                                copy per resident block fits the SM; 0 = always read the byte map from global memory */
-  RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 1 (default) = every warp draws its next work bundle on its own;
-                               > 1 = the warps of a block draw together and meet at the block barrier per draw */
+  RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 0 = every warp draws its next work bundle on its own; k >= 1 = the warps of a
+                               block draw k bundles each together and meet at the block barrier per draw; -1 = default */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */

@@ -78,7 +78,7 @@ struct rm_ctx {
   unsigned long long queue_base = 0;      // expected value of d_queue[1] (monotonic, rm_launch_render_persist)
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
   int persist_smem = 1;                   // stage the 4-bit distance map into shared memory when it fits (RM_OPT_PERSIST_SMEM)
-  int persist_group = 1;                  // warps of the default kernel that draw bundles together (RM_OPT_PERSIST_GROUP)
+  int persist_group = -1;                 // bundles per warp per block-synchronous round of the default kernel; 0 = free-running; -1 = default
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
   int warp_blocks[2] = {0, 0};            // resident blocks per SM of the warp kernel [plain, counting]
@@ -383,8 +383,11 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
         } else if (c->kernel_kind == 0) {
           int packed = 0;
           uint32_t* argb = fused_argb_target(c, &packed);
+          // defaults (measured on B200, C2): 256 x 5 blocks with block-synchronous rounds
+          const int persist_block = c->persist_block ? c->persist_block : RM_PERSIST_DEFAULT_BLOCK;
+          const int persist_group = c->persist_group >= 0 ? c->persist_group : RM_PERSIST_DEFAULT_ROUND;
           e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
-                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, c->persist_block, c->persist_group, c->persist_smem, c->stream);
+                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, persist_block, persist_group, c->persist_smem, c->stream);
           launched = 1;
           if (e == cudaSuccess && argb) {
             c->argb_fresh_ptr = argb;
@@ -1143,15 +1146,15 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
       c->trip_limit = (unsigned)value;
       return RM_OK;
     case RM_OPT_PERSIST_BLOCK:
-      if (value != 0 && value != 256 && value != 1024)
-        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 1024 (x 1 block per SM) or 256 (x 5) threads");
+      if (value != 0 && value != 128 && value != 256 && value != 1024)
+        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 1024 (x 1 block per SM), 256 (x 5) or 128 (x 10) threads");
       c->persist_block = (int)value;
       return RM_OK;
     case RM_OPT_PERSIST_SMEM:
       c->persist_smem = value != 0;
       return RM_OK;
     case RM_OPT_PERSIST_GROUP:
-      if (value < 1 || value > 32) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_GROUP: 1..32 warps");
+      if (value < -1 || value > 64) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_GROUP: -1 (default), 0 (free-running warps) or 1..64 bundles per warp per round");
       c->persist_group = (int)value;
       return RM_OK;
     case RM_OPT_FUSE_LIMIT:

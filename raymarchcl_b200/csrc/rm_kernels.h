@@ -69,6 +69,8 @@ cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, i
 // ---- default kernel: persistent warps, distance map in shared memory, blend + tonemap folded in
 // (rm_scene_fused.cuh, rm_render_persist.cu), RM_OPT_KERNEL = 0 ----
 #define RM_PERSIST_MAX_SMEM (200 * 1024) // largest 4-bit distance map staged into shared memory
+#define RM_PERSIST_DEFAULT_BLOCK 256      // measured best layout on B200 (C2): 256 threads x 5 blocks per SM ...
+#define RM_PERSIST_DEFAULT_ROUND 1        // ... drawing bundles in block-synchronous rounds
 // How many of `available` consecutive fusable passes one launch should take: all (<= 32) when they
 // fill >= 80 % of a warp's lanes as whole pixels x passes groups, else the largest power of two.
 int rm_persist_pick_passes(int available);
@@ -78,12 +80,12 @@ int rm_persist_pick_passes(int available);
 // counter owned by the context, *queue_base its expected value (updated by this call; never reset).
 // block_threads: layout of the resident blocks: 1024 (x 1 per SM, 64 registers) or 256 (x 5 per SM, 48 registers).
 // smem_map: 0 = read the distance map from global memory even when the 4-bit copy would fit the SM's shared memory.
-// group_warps: > 1 = the warps of a block draw their bundles together and meet at the block barrier per draw (1 = free-running).
+// round_bundles: 0 = free-running warps; k = the block draws warps x k bundles together and meets at its barrier per draw.
 cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
-                                     int block_threads, int group_warps, int smem_map, cudaStream_t stream);
+                                     int block_threads, int round_bundles, int smem_map, cudaStream_t stream);
 
 // ---- warp-scheduled state machine (rm_render_warp.cu), RM_OPT_KERNEL = 2 ----
 int rm_warp_blocks_per_sm(int count);

@@ -45,7 +45,7 @@ struct PersistParams {
   int ppb;                           // pixels per bundle = 32 / m
   const uint8_t* nib;                // 4-bit distance map in global memory (source of the bulk copy)
   unsigned nib_bytes;                // multiple of 16
-  int group_warps;                   // warps that draw their bundles together (1 = every warp on its own)
+  int round_bundles;                 // 0 = free-running warps; k = block-synchronous rounds of k bundles per warp
 };
 
 // tonemap + pack of one pixel (renderer.cl:448-454, :502-506); same expression as rm_kernels.cu
@@ -106,31 +106,41 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
   s.table = P.tables + (size_t)(lane_used ? pass : 0) * (RM_TABLE_MASK + 1);
   s.time = P.times[lane_used ? pass : 0];
 
-  // Scheduling granularity. group_warps == 1: every warp draws its next bundle on its own (no warp ever
-  // waits for another). group_warps == warps of the block: the block draws that many consecutive bundles
-  // together and meets at the block barrier before the next draw, like a non-persistent block of the
-  // per-item kernel -- its warps then run the same phases of the routine at the same time and share the
-  // instruction cache lines they pull in. (Groups smaller than the block were measured too, over named
-  // barriers: no better, and a dynamic barrier id makes ptxas reserve all 16 barriers, which caps the
-  // 256-thread layout at 4 resident blocks.)
+  // Scheduling granularity (round_bundles, RM_OPT_PERSIST_GROUP).
+  //   0: every warp draws its next bundle on its own -- no warp ever waits for another, but the warps of
+  //      an SM drift through the routine independently and the kernel's code (2x the 32 KB L1.5 instruction
+  //      cache, ~40 KB of it touched once per bundle) is fetched again and again: ncu stall_no_instruction
+  //      2.2 - 3.0 per issue.
+  //   k: the block draws (its warps) x k consecutive bundles together, warp w takes bundles w, w + W, ...
+  //      and the block meets at its barrier before the next draw. Its warps then run the same phases of
+  //      the routine at about the same time and share the instruction lines they pull in (stall_no_instruction
+  //      0.9), at the price of waiting for the slowest warp of a round; larger k = fewer, relatively
+  //      shorter waits but more drift.
   __shared__ unsigned long long s_ticket[2];
-  const bool grouped = P.group_warps > 1;
+  const int K = P.round_bundles;
+  constexpr int W = kThreads / 32;
   const int warp = (int)(threadIdx.x >> 5);
   unsigned round = 0;
+  unsigned long long t0 = 0;
+  int in_round = K;
   for (;;) {
     unsigned long long t = 0;
-    if (!grouped) {
+    if (K == 0) {
       if (lane == 0) t = atomicAdd(P.queue, 1ull) - P.queue_base;
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= (unsigned long long)P.bundles) break;
     } else {
-      if (threadIdx.x == 0) s_ticket[round & 1u] = atomicAdd(P.queue, (unsigned long long)(kThreads / 32)) - P.queue_base;
-      __syncthreads();
-      const unsigned long long t0 = s_ticket[round & 1u];
-      ++round;
-      if (t0 >= (unsigned long long)P.bundles) break;  // the whole block leaves together
-      t = t0 + (unsigned)warp;
-      if (t >= (unsigned long long)P.bundles) continue;  // ragged last draw: sit this round out
+      if (in_round == K) {
+        if (threadIdx.x == 0) s_ticket[round & 1u] = atomicAdd(P.queue, (unsigned long long)(W * K)) - P.queue_base;
+        __syncthreads();
+        t0 = s_ticket[round & 1u];
+        ++round;
+        in_round = 0;
+        if (t0 >= (unsigned long long)P.bundles) break;  // the whole block leaves together
+      }
+      t = t0 + (unsigned)(warp + W * in_round);
+      ++in_round;
+      if (t >= (unsigned long long)P.bundles) continue;  // ragged last draw: sit this one out
     }
     const long long slot = (long long)t * P.ppb + sub;
     const bool in_shard = lane_used && slot < sh.slots;
@@ -174,12 +184,12 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
 }
 
 // function attributes are per device: set once per (device, instantiation)
-std::once_flag g_attr_once[64][16];
+std::once_flag g_attr_once[64][24];
 
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 cudaError_t launch(const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev, cudaStream_t stream) {
   cudaError_t attr = cudaSuccess;
-  constexpr int variant = ((kThreads == 1024 ? 0 : 1) << 3) | (kCount ? 4 : 0) | kMap;
+  constexpr int variant = ((kThreads == 1024 ? 0 : (kThreads == 256 ? 1 : 2)) << 3) | (kCount ? 4 : 0) | kMap;
   std::call_once(g_attr_once[dev & 63][variant], [&] {
     if (kMap & fused::kMapNib) attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PERSIST_MAX_SMEM / kBlocksPerSM);
     else attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -194,6 +204,7 @@ cudaError_t launch_any(bool count, int threads, const RmShard& shard, const Pers
                        cudaStream_t stream) {
   if (count) return launch<true, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
   if (threads == 256) return launch<false, kMap, 256, 5>(shard, P, blocks, smem, dev, stream);
+  if (threads == 128) return launch<false, kMap, 128, 10>(shard, P, blocks, smem, dev, stream);
   return launch<false, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
 }
 
@@ -212,7 +223,7 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
-                                     int block_threads, int group_warps, int smem_map, cudaStream_t stream) {
+                                     int block_threads, int round_bundles, int smem_map, cudaStream_t stream) {
   if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
   if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
   PersistParams P;
@@ -233,15 +244,16 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
   P.nib = accel.nib;
   P.nib_bytes = accel.nib_bytes;
-  const int threads = d_counters ? 1024 : (block_threads == 256 ? 256 : 1024);
-  const int blocks_per_sm = threads == 1024 ? 1 : 5;
+  const int threads = d_counters ? 1024 : (block_threads == 256 || block_threads == 128 ? block_threads : 1024);
+  const int blocks_per_sm = threads == 1024 ? 1 : (threads == 256 ? 5 : 10);
   const bool use_nib = smem_map != 0 && accel.nib != nullptr && accel.nib_bytes > 0 &&
                        accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
   const int warps_per_block = threads / 32;
   long long blocks = (P.bundles + warps_per_block - 1) / warps_per_block;
   if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;
-  const int G = group_warps > 1 ? warps_per_block : 1;  // block-synchronous draws, or free-running warps
-  P.group_warps = G;
+  const int K = round_bundles < 0 ? 0 : (round_bundles > 64 ? 64 : round_bundles);
+  P.round_bundles = K;
+  const int G = K > 0 ? warps_per_block * K : 1;  // tickets per draw
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;

@@ -11,15 +11,22 @@ run() {
   echo "$name: $(python -c "import json;d=json.load(open('gpurun_out/${TAG}_${name}.json'));print(round(d['ms_per_step'],3), round(d['roofline']['kernel_ms_per_frame'],3))" 2>&1 | tail -1)"
 }
 run bricks --kernel bricks
-run b1024_smem --opt 10=1024 --opt 12=1
-run b1024_glob --opt 10=1024 --opt 12=0
-run b256_glob --opt 10=256 --opt 12=0
-run b256_g8 --opt 10=256 --opt 12=0 --opt 11=8
-run b1024_g32 --opt 10=1024 --opt 12=1 --opt 11=32
-for V in ${NCU_VARIANTS:-"1024,1 256,0"}; do
-  B=${V%,*}; S=${V#*,}
+if [ "${SKIP_AB:-0}" != "1" ]; then
+run b256_k0 --opt 10=256 --opt 12=0 --opt 11=0
+run b256_k1 --opt 10=256 --opt 12=0 --opt 11=1
+run b256_k2 --opt 10=256 --opt 12=0 --opt 11=2
+run b256_k4 --opt 10=256 --opt 12=0 --opt 11=4
+run b128_k1 --opt 10=128 --opt 12=0 --opt 11=1
+run b128_k2 --opt 10=128 --opt 12=0 --opt 11=2
+run b128_k4 --opt 10=128 --opt 12=0 --opt 11=4
+run b1024_k0 --opt 10=1024 --opt 12=1 --opt 11=0
+fi
+ncu_cap() {  # block, smem, group
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_persist -s 1 -c 1 -f \
-    -o gpurun_out/${TAG}_persist_b${B}_c2 python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity \
-    --opt 10=$B --opt 12=$S > gpurun_out/${TAG}_ncu_b$B.log 2>&1
-  echo "ncu b$B rc=$?"
-done
+    -o gpurun_out/${TAG}_persist_b$1_s$2_g$3_c2 python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity \
+    --opt 10=$1 --opt 12=$2 --opt 11=$3 > gpurun_out/${TAG}_ncu_b$1_g$3.log 2>&1
+  echo "ncu b$1 s$2 g$3 rc=$?"
+}
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+  for v in ${NCU_CAPS:-256,0,1}; do IFS=, read b s g <<< "$v"; ncu_cap $b $s $g; done
+fi
