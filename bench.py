@@ -54,7 +54,8 @@ WORKLOADS = {
     "c5": dict(name="1024^3 thin-blob stand-in, 1920x1080, 16 passes, :metal2 (BASELINE configs[4] stand-in)",
                scene=dict(vres=1024, width=1920, height=1080, iters=16, mat="metal2", volume="dragon")),
 }
-TILE = (32, 32)
+TILE = (32, 32)       # one GPU: only the order in which the warps walk the frame
+TILE_SHARDED = (16, 8)  # several GPUs: small tiles in diagonal stripes, 0.2 % load imbalance at 8 ranks
 L2_FLUSH_BYTES = 512 << 20  # > 126 MB L2
 
 
@@ -298,6 +299,9 @@ def run_b200(args):
     mcs_pinned = [torch.from_numpy(np.ascontiguousarray(m)).pin_memory() for m in mcs]
     mcs_host = [m.numpy() for m in mcs_pinned]
 
+    global TILE
+    if world > 1:
+        TILE = TILE_SHARDED
     layout = ShardLayout(w, h, world, *TILE)
     r = Renderer(local)
     r.set_option(_lib.RM_OPT_KERNEL, {"fast": 0, "plain": 1, "warp": 2, "wave": 3, "bricks": 4}[args.kernel])
@@ -407,8 +411,25 @@ def run_b200(args):
             if world == 1:
                 r.set_argb_target(None)  # rm_tonemap reads the context's own frame, which the render launch then fills
 
+            dvol = dslab = None
+            if world > 1 and vol.size % world == 0:
+                # every rank uploads 1/N of the volume over ITS PCIe link; one all-gather over NVLink completes it
+                dvol = torch.empty(vol.size, dtype=torch.uint8, device=dev)
+                chunk = vol.size // world
+                dslab = torch.empty(chunk, dtype=torch.uint8, device=dev)
+                vol_flat = vol_pinned.reshape(-1)
+
+            def upload_volume():
+                if dvol is None:
+                    r.set_volume(vol_host)
+                    return
+                dslab.copy_(vol_flat[rank * chunk:(rank + 1) * chunk], non_blocking=True)
+                dist.all_gather_into_tensor(dvol, dslab)
+                rz, ry, rx = vol.shape
+                r.set_volume_device(dvol.data_ptr(), rx, ry, rz)
+
             def host_frame():
-                r.set_volume(vol_host)
+                upload_volume()
                 r.clear_accum(w, h)
                 r.render_frame(opts, mcs_host)
                 if world == 1:
@@ -432,12 +453,14 @@ def run_b200(args):
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e_s = te.item()
-            h2d = vol.size + iters * (65536 * 4 + 544)
+            h2d = (vol.size if dvol is None else vol.size // world) * world + world * iters * (65536 * 4 + 544)
             e2e = {"value": steps_frame * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s",
                    "frames_per_s": args.steps / e2e_s, "ms_per_step": 1e3 * e2e_s / args.steps,
-                   "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(w * h * 4),
-                   "path": "rm_set_volume + rm_clear_accum + rm_render_frame + rm_tonemap, pinned host buffers"
-                           + ("" if world == 1 else "; every rank uploads its own copy of the inputs")}
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(w * h * 4),
+                   "path": "rm_set_volume + rm_clear_accum + rm_render_frame + rm_tonemap, pinned host buffers" if world == 1 else
+                           "per rank: 1/N of the volume over its own PCIe link + NCCL all-gather + rm_set_volume_device, "
+                           "rm_clear_accum, rm_render_frame (own copy of the tables), ARGB written by the render launch into "
+                           "the gather buffer, one NCCL gather + rm_unpack_shards, D2H of the frame on rank 0"}
 
     if rank != 0:
         if world > 1:

@@ -75,7 +75,6 @@ struct rm_ctx {
   int num_sms = 0;
   cudaEvent_t launch_done = nullptr;  // completion of this context's last render launch (DeviceGuard)
   unsigned long long* d_queue = nullptr;  // [0] work queue head of the warp kernel, [1] bundle tickets of the default kernel
-  unsigned long long queue_base = 0;      // expected value of d_queue[1] (monotonic, rm_launch_render_persist)
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
   int persist_smem = 1;                   // stage the 4-bit distance map into shared memory when it fits (RM_OPT_PERSIST_SMEM)
   int persist_group = -1;                 // bundles per warp per block-synchronous round of the default kernel; 0 = free-running; -1 = default
@@ -387,7 +386,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
           const int persist_block = c->persist_block ? c->persist_block : RM_PERSIST_DEFAULT_BLOCK;
           const int persist_group = c->persist_group >= 0 ? c->persist_group : RM_PERSIST_DEFAULT_ROUND;
           e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
-                                       argb, packed, cnt, c->d_queue + 1, &c->queue_base, c->num_sms, persist_block, persist_group, c->persist_smem, c->stream);
+                                       argb, packed, cnt, c->d_queue + 1, c->num_sms, persist_block, persist_group, c->persist_smem, c->stream);
           launched = 1;
           if (e == cudaSuccess && argb) {
             c->argb_fresh_ptr = argb;

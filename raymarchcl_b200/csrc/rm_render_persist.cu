@@ -38,8 +38,7 @@ struct PersistParams {
   float gamma;
   int argb_packed;                   // argb is indexed by shard slot (else by pixel id)
   RmCounters* counters;
-  unsigned long long* queue;         // bundle tickets: monotonic across launches, see rm_launch_render_persist
-  unsigned long long queue_base;
+  unsigned long long* queue;         // bundle tickets (zeroed before the launch)
   long long bundles;
   int passes;                        // m
   int ppb;                           // pixels per bundle = 32 / m
@@ -126,12 +125,12 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
   for (;;) {
     unsigned long long t = 0;
     if (K == 0) {
-      if (lane == 0) t = atomicAdd(P.queue, 1ull) - P.queue_base;
+      if (lane == 0) t = atomicAdd(P.queue, 1ull);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= (unsigned long long)P.bundles) break;
     } else {
       if (in_round == K) {
-        if (threadIdx.x == 0) s_ticket[round & 1u] = atomicAdd(P.queue, (unsigned long long)(W * K)) - P.queue_base;
+        if (threadIdx.x == 0) s_ticket[round & 1u] = atomicAdd(P.queue, (unsigned long long)(W * K));
         __syncthreads();
         t0 = s_ticket[round & 1u];
         ++round;
@@ -222,7 +221,7 @@ int rm_persist_pick_passes(int available) {
 cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
-                                     unsigned long long* d_queue, unsigned long long* queue_base, int num_sms,
+                                     unsigned long long* d_queue, int num_sms,
                                      int block_threads, int round_bundles, int smem_map, cudaStream_t stream) {
   if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
   if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
@@ -238,7 +237,6 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   P.argb_packed = argb_packed;
   P.counters = d_counters;
   P.queue = d_queue;
-  P.queue_base = *queue_base;
   P.passes = passes;
   P.ppb = 32 / passes;
   P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
@@ -253,12 +251,12 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;
   const int K = round_bundles < 0 ? 0 : (round_bundles > 64 ? 64 : round_bundles);
   P.round_bundles = K;
-  const int G = K > 0 ? warps_per_block * K : 1;  // tickets per draw
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbolAsync(fused::g_opts, &opts, sizeof(RmOpts), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbolAsync(fused::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
   const size_t smem = use_nib ? accel.nib_bytes : 0;
   const int map = (use_nib ? fused::kMapNib : 0) | (accel.cell_shift == 2 ? fused::kMapCell4 : 0);
   const bool cnt = d_counters != nullptr;
@@ -269,8 +267,5 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
     default: e = launch_any<3>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
   }
   if (e != cudaSuccess) return e;
-  // Every warp (group of G warps) of the grid draws tickets, G at a time, until it draws one past the end:
-  // ceil(bundles / G) successful draws plus exactly one failing draw per group.
-  *queue_base += (unsigned long long)G * (unsigned long long)((P.bundles + G - 1) / G + blocks * (warps_per_block / G));
   return cudaSuccess;
 }
