@@ -132,9 +132,9 @@ def parity_check(oracle_lib, vol, mcs, opts, w, h, accum, argb, stride):
 
 def counters_check(r, oracle_lib, vol, mcs, opts, w, h, iters, rank, world, resident_render):
     """The metric's numerator is the kernel's own step counter: pin it. The counting kernel renders the tiles
-    of one shard of 64 and must report exactly the oracle's inner-step / tap / sphere-trace counts there."""
+    of one shard of `sub` (64 at C2) and must report exactly the oracle's inner-step / tap / sphere-trace counts there."""
     from raymarchcl_b200.dist import ShardLayout
-    sub = 64
+    sub = max(1, (w * h * iters) // 520_000)
     idx = ShardLayout(w, h, sub, *TILE).slot_pixel_index(0)
     ids = np.sort(idx[idx >= 0]).astype(np.int32)
     r.set_tile_shard(0, sub, *TILE)
@@ -247,7 +247,7 @@ def run_reference(args):
     ref, kind, name = cpu_reference()
     cores = host_threads()
     ref.set_num_threads(cores)
-    stride = 16 if w * h * iters > 4_000_000 else 1
+    stride = max(1, (w * h * iters) // 2_000_000)  # C2: every 16th pixel id
     ids = cpu_sample_ids(w, h, stride)
     steps_sample, taps_sample = count_sample_steps(vol, mcs, opts, w, h, ids)
     for _ in range(args.warmup):
@@ -394,7 +394,9 @@ def run_b200(args):
             from oracle import build_oracle, refso
             build_oracle.build(verbose=False)
             orc = refso.load("oracle")
-            stride = 64 if w * h * iters > 4_000_000 else 1
+            # ~520 k pixel-samples for the oracle (about a second on 16 cores): every 64th pixel of C2
+            stride = max(1, (w * h * iters) // 520_000)
+            stride = 1 if stride < 2 else (stride // 64 * 64 if stride >= 64 else stride)
             if rank == 0:
                 parity = parity_check(orc, vol, mcs, opts, w, h, accum_last, argb_last, stride)
             ok, npx = counters_check(r, orc, vol, mcs, opts, w, h, iters, rank, world, resident_frame) if rank == 0 else (True, 0)
@@ -521,7 +523,7 @@ def run_b200(args):
             ref, kind, name = cpu_reference()
             cores = host_threads()
             ref.set_num_threads(cores)
-            stride = 4 if w * h * iters > 4_000_000 else 1
+            stride = max(1, (w * h * iters) // 8_000_000)  # C2: every 4th pixel id
             ids = cpu_sample_ids(w, h, stride)
             s_steps, _ = count_sample_steps(vol, mcs, opts, w, h, ids)
             tcpu = time_cpu(ref, vol, mcs, opts, w, h, ids)
