@@ -89,6 +89,8 @@ typedef enum rm_option {
                                or 256 (x 5, 48 registers) threads */
   RM_OPT_PERSIST_SMEM = 12,  /* kernel 0: 1 (default) = stage the 4-bit distance map into shared memory by bulk TMA when a
                                copy per resident block fits the SM; 0 = always read the byte map from global memory */
+  RM_OPT_PERSIST_ORDER = 13, /* kernel 0: 1 (default) = walk the frame bottom-up so that the launch ends on the (cheap) top rows; 0 = top-down */
+  RM_OPT_PERSIST_HALVES = 14, /* kernel 0, round mode: 1 = the two halves of a block draw and synchronise separately; 0 (default) */
   RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 0 = every warp draws its next work bundle on its own; k >= 1 = the warps of a
                                block draw k bundles each together and meet at the block barrier per draw; -1 = default */
 } rm_option;

@@ -76,6 +76,8 @@ struct rm_ctx {
   cudaEvent_t launch_done = nullptr;  // completion of this context's last render launch (DeviceGuard)
   unsigned long long* d_queue = nullptr;  // [0] work queue head of the warp kernel, [1] bundle tickets of the default kernel
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
+  int persist_bottom_up = 1;              // RM_OPT_PERSIST_ORDER
+  int persist_halves = 0;                 // RM_OPT_PERSIST_HALVES
   int persist_smem = 1;                   // stage the 4-bit distance map into shared memory when it fits (RM_OPT_PERSIST_SMEM)
   int persist_group = -1;                 // bundles per warp per block-synchronous round of the default kernel; 0 = free-running; -1 = default
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
@@ -386,7 +388,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
           const int persist_block = c->persist_block ? c->persist_block : RM_PERSIST_DEFAULT_BLOCK;
           const int persist_group = c->persist_group >= 0 ? c->persist_group : RM_PERSIST_DEFAULT_ROUND;
           e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
-                                       argb, packed, cnt, c->d_queue + 1, c->num_sms, persist_block, persist_group, c->persist_smem, c->stream);
+                                       argb, packed, cnt, c->d_queue + 1, c->num_sms, persist_block, persist_group, c->persist_smem, c->persist_bottom_up, c->persist_halves, c->stream);
           launched = 1;
           if (e == cudaSuccess && argb) {
             c->argb_fresh_ptr = argb;
@@ -1148,6 +1150,12 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
       if (value != 0 && value != 128 && value != 256 && value != 1024)
         return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 1024 (x 1 block per SM), 256 (x 5) or 128 (x 10) threads");
       c->persist_block = (int)value;
+      return RM_OK;
+    case RM_OPT_PERSIST_HALVES:
+      c->persist_halves = value != 0;
+      return RM_OK;
+    case RM_OPT_PERSIST_ORDER:
+      c->persist_bottom_up = value != 0;
       return RM_OK;
     case RM_OPT_PERSIST_SMEM:
       c->persist_smem = value != 0;

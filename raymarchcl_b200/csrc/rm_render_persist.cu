@@ -45,6 +45,8 @@ struct PersistParams {
   const uint8_t* nib;                // 4-bit distance map in global memory (source of the bulk copy)
   unsigned nib_bytes;                // multiple of 16
   int round_bundles;                 // 0 = free-running warps; k = block-synchronous rounds of k bundles per warp
+  int bottom_up;                     // hand the bundles out last-to-first
+  int half_groups;                   // round mode: the two halves of a block draw / synchronise separately
 };
 
 // tonemap + pack of one pixel (renderer.cl:448-454, :502-506); same expression as rm_kernels.cu
@@ -115,10 +117,15 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
   //      the routine at about the same time and share the instruction lines they pull in (stall_no_instruction
   //      0.9), at the price of waiting for the slowest warp of a round; larger k = fewer, relatively
   //      shorter waits but more drift.
-  __shared__ unsigned long long s_ticket[2];
+  __shared__ unsigned long long s_ticket[2][2];
   const int K = P.round_bundles;
-  constexpr int W = kThreads / 32;
-  const int warp = (int)(threadIdx.x >> 5);
+  // half_groups: the two halves of the block (warps 0..W/2-1 and W/2..W-1) draw and synchronise separately,
+  // over named barriers 1 and 2 (constant ids: ptxas reserves 3 barriers, not 16)
+  const bool halves = P.half_groups != 0 && kThreads >= 128;
+  const int W = halves ? kThreads / 64 : kThreads / 32;
+  const int warp_all = (int)(threadIdx.x >> 5);
+  const int half = halves && warp_all >= W ? 1 : 0;
+  const int warp = warp_all - half * W;
   unsigned round = 0;
   unsigned long long t0 = 0;
   int in_round = K;
@@ -130,17 +137,24 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
       if (t >= (unsigned long long)P.bundles) break;
     } else {
       if (in_round == K) {
-        if (threadIdx.x == 0) s_ticket[round & 1u] = atomicAdd(P.queue, (unsigned long long)(W * K));
-        __syncthreads();
-        t0 = s_ticket[round & 1u];
+        if (warp == 0 && lane == 0) s_ticket[half][round & 1u] = atomicAdd(P.queue, (unsigned long long)(W * K));
+        if (!halves) __syncthreads();
+        else if (half == 0) asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"r"(W * 32) : "memory");
+        t0 = s_ticket[half][round & 1u];
         ++round;
         in_round = 0;
-        if (t0 >= (unsigned long long)P.bundles) break;  // the whole block leaves together
+        if (t0 >= (unsigned long long)P.bundles) break;  // the whole group leaves together
       }
       t = t0 + (unsigned)(warp + W * in_round);
       ++in_round;
       if (t >= (unsigned long long)P.bundles) continue;  // ragged last draw: sit this one out
     }
+    // Bundles are handed out from the END of the shard's slot list, i.e. the frame is walked bottom-up: the
+    // launch then ends on the top rows of the image, which in this renderer's scenes are mostly sky -- the
+    // cheapest bundles there are -- so that the SMs drain within microseconds of each other instead of
+    // within one expensive bundle (a pure scheduling choice: every bundle is rendered exactly once either way).
+    if (P.bottom_up) t = (unsigned long long)P.bundles - 1ull - t;
     const long long slot = (long long)t * P.ppb + sub;
     const bool in_shard = lane_used && slot < sh.slots;
     const int id = in_shard ? rm_slot_to_pixel(sh, slot, o.width, o.height) : -1;
@@ -222,7 +236,7 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, int num_sms,
-                                     int block_threads, int round_bundles, int smem_map, cudaStream_t stream) {
+                                     int block_threads, int round_bundles, int smem_map, int bottom_up, int half_groups, cudaStream_t stream) {
   if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
   if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
   PersistParams P;
@@ -251,6 +265,8 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;
   const int K = round_bundles < 0 ? 0 : (round_bundles > 64 ? 64 : round_bundles);
   P.round_bundles = K;
+  P.bottom_up = bottom_up != 0;
+  P.half_groups = half_groups != 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
