@@ -129,6 +129,8 @@ cudaError_t rm_accel_build(const uint8_t* d_vox, int rx, int ry, int rz, int iso
   const int cell = 1 << a.cell_shift;
   a.cellf = (float)cell;
   a.rxf = (float)rx; a.ryf = (float)ry; a.rzf = (float)rz;
+  a.inv_rxf = 1.0f / a.rxf; a.inv_ryf = 1.0f / a.ryf; a.inv_rzf = 1.0f / a.rzf;
+  a.pow2 = ((rx & (rx - 1)) == 0 && (ry & (ry - 1)) == 0 && (rz & (rz - 1)) == 0) ? 1 : 0;
   a.mx = (rx + cell - 1) >> a.cell_shift; a.my = (ry + cell - 1) >> a.cell_shift; a.mz = (rz + cell - 1) >> a.cell_shift;
   const size_t nb = (size_t)a.bx * a.by * a.bz, nc = (size_t)a.mx * a.my * a.mz;
   cudaError_t e;

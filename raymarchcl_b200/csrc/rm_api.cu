@@ -1147,8 +1147,8 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
       c->trip_limit = (unsigned)value;
       return RM_OK;
     case RM_OPT_PERSIST_BLOCK:
-      if (value != 0 && value != 128 && value != 256 && value != 1024)
-        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 1024 (x 1 block per SM), 256 (x 5) or 128 (x 10) threads");
+      if (value != 0 && value != 256 && value != 1024)
+        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 1024 (x 1 block per SM) or 256 (x 5) threads");
       c->persist_block = (int)value;
       return RM_OK;
     case RM_OPT_PERSIST_HALVES:

@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
 // Layouts (threads per block x resident blocks per SM), RM_OPT_PERSIST_BLOCK: 1024 x 1 (64 registers,
 // 32 warps per SM, room for a 200 KB distance map) and 256 x 5 (48 registers, 40 warps, <= 40 KB map per
 // block). Every block stages its own copy of the map, so the 128 KiB map of a 256^3 volume only fits
-// the first layout. (640 x 2 at 48 registers was measured too: like 1024 x 1.)
+// the first layout. (640 x 2 at 48 registers was measured too: like 1024 x 1; 128 x 10: 15 % slower.)
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ PersistParams P) {
@@ -197,12 +197,12 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
 }
 
 // function attributes are per device: set once per (device, instantiation)
-std::once_flag g_attr_once[64][24];
+std::once_flag g_attr_once[64][32];
 
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 cudaError_t launch(const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev, cudaStream_t stream) {
   cudaError_t attr = cudaSuccess;
-  constexpr int variant = ((kThreads == 1024 ? 0 : (kThreads == 256 ? 1 : 2)) << 3) | (kCount ? 4 : 0) | kMap;
+  constexpr int variant = ((kThreads == 1024 ? 0 : 1) << 4) | (kCount ? 8 : 0) | kMap;
   std::call_once(g_attr_once[dev & 63][variant], [&] {
     if (kMap & fused::kMapNib) attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PERSIST_MAX_SMEM / kBlocksPerSM);
     else attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -215,9 +215,9 @@ cudaError_t launch(const RmShard& shard, const PersistParams& P, int blocks, siz
 template <int kMap>
 cudaError_t launch_any(bool count, int threads, const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev,
                        cudaStream_t stream) {
-  if (count) return launch<true, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
+  // (the counting kernels visit every sample anyway: only the map's location matters to them)
+  if (count) return launch<true, kMap & fused::kMapNib, 1024, 1>(shard, P, blocks, smem, dev, stream);
   if (threads == 256) return launch<false, kMap, 256, 5>(shard, P, blocks, smem, dev, stream);
-  if (threads == 128) return launch<false, kMap, 128, 10>(shard, P, blocks, smem, dev, stream);
   return launch<false, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
 }
 
@@ -256,8 +256,8 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
   P.nib = accel.nib;
   P.nib_bytes = accel.nib_bytes;
-  const int threads = d_counters ? 1024 : (block_threads == 256 || block_threads == 128 ? block_threads : 1024);
-  const int blocks_per_sm = threads == 1024 ? 1 : (threads == 256 ? 5 : 10);
+  const int threads = d_counters ? 1024 : (block_threads == 256 ? 256 : 1024);
+  const int blocks_per_sm = threads == 1024 ? 1 : 5;
   const bool use_nib = smem_map != 0 && accel.nib != nullptr && accel.nib_bytes > 0 &&
                        accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
   const int warps_per_block = threads / 32;
@@ -274,13 +274,17 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   if ((e = cudaMemcpyToSymbolAsync(fused::g_accel, &accel, sizeof(RmAccel), 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
   const size_t smem = use_nib ? accel.nib_bytes : 0;
-  const int map = (use_nib ? fused::kMapNib : 0) | (accel.cell_shift == 2 ? fused::kMapCell4 : 0);
+  const int map = (use_nib ? fused::kMapNib : 0) | (accel.cell_shift == 2 ? fused::kMapCell4 : 0) | (accel.pow2 ? fused::kMapPow2 : 0);
   const bool cnt = d_counters != nullptr;
   switch (map) {
     case 0: e = launch_any<0>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
     case 1: e = launch_any<1>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
     case 2: e = launch_any<2>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
-    default: e = launch_any<3>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    case 3: e = launch_any<3>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    case 4: e = launch_any<4>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    case 5: e = launch_any<5>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    case 6: e = launch_any<6>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
+    default: e = launch_any<7>(cnt, threads, shard, P, (int)blocks, smem, dev, stream); break;
   }
   if (e != cudaSuccess) return e;
   return cudaSuccess;

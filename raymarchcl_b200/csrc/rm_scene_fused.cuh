@@ -86,11 +86,12 @@ struct Isec {  // TIsec, renderer.cl:6-12
 };
 
 struct Hit {  // one distanceToScene call (renderer.cl:209-237) without its normal
-  float3 p;      // sample position of the solid voxel the march stopped on (when hit)
+  float3 p;      // sample position of the solid voxel the march stopped on (when kHit)
   float dist;    // .x of the returned pair
-  bool hit;      // the march stopped on a solid voxel
-  bool closer;   // ... and the voxel distance won against the ground plane
+  int flags;     // kHit: the march stopped on a solid voxel; kCloser: ... and the voxel distance won against the
+                 // ground plane. (One word: two bools in a struct cost a dozen byte-permutes per sphere-trace trip.)
 };
+enum { kHit = 1, kCloser = 2 };
 
 RM_DEV float4 table_at(const Lane& s, uint32_t seed) { return __ldg(s.table + (seed & RM_TABLE_MASK)); }
 RM_DEV float3 table_xyz(const Lane& s, uint32_t seed) {
@@ -129,7 +130,9 @@ RM_DEV int voxel_value(int x, int y, int z) {
 //   kMapNib    the 4-bit copy in shared memory (else the byte map in global memory)
 //   kMapCell4  the macro-cell is one 4x4x4 brick (cell_shift == 2: every volume up to 256^3), so the cell
 //              index is the brick index and the shift is an immediate
-enum { kMapNib = 1, kMapCell4 = 2 };
+//   kMapPow2   every grid extent is a power of two: the march runs its recurrence in voxel units (exact, see
+//              march_fast) and saves the three multiplies per sample
+enum { kMapNib = 1, kMapCell4 = 2, kMapPow2 = 4 };
 // Chebyshev distance (in macro-cells, saturated) from the cell of voxel (x, y, z) to the nearest cell
 // that holds a solid voxel.
 template <int kMap>
@@ -223,14 +226,25 @@ template <int kMap>
 RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
   RM_STAT_MARCH();
   const float A = g_accel.cellf * invS, B = 0.25f * invS + 0.5f;  // invS <= 2000 (march_delta)
+  // Power-of-two grids: q = p * res and dq = delta * res are exact (a change of exponent), and so is every
+  // q += dq against p += delta -- fl((a + b) * 2^k) = fl(a + b) * 2^k as long as nothing is subnormal, and a sum
+  // of two such floats is either 0 or no smaller than an ulp of the larger one. The sample's voxel is then
+  // trunc(q) with no multiply, and p = q / res (exact again) is handed back at the end.
+  constexpr bool kPow2 = (kMap & kMapPow2) != 0;
   float px = p.x, py = p.y, pz = p.z;
+  if (kPow2) {
+    px *= g_accel.rxf; py *= g_accel.ryf; pz *= g_accel.rzf;
+    delta = f3(delta.x * g_accel.rxf, delta.y * g_accel.ryf, delta.z * g_accel.rzf);
+  }
   bool found = false;
   const unsigned nib = (kMap & kMapNib) ? nib_base() : 0u;
-  const float rxf = g_accel.rxf, ryf = g_accel.ryf, rzf = g_accel.rzf;
+  const float rxf = kPow2 ? 1.0f : g_accel.rxf, ryf = kPow2 ? 1.0f : g_accel.ryf, rzf = kPow2 ? 1.0f : g_accel.rzf;
   const unsigned rx = g_opts.rx, ry = g_opts.ry, rz = g_opts.rz;
   const int cs = (kMap & kMapCell4) ? 2 : g_accel.cell_shift, my = g_accel.my, mx = g_accel.mx;
   while (rem > 0) {
-    const int x = f2i_sat(px * rxf), y = f2i_sat(py * ryf), z = f2i_sat(pz * rzf);
+    const int x = kPow2 ? f2i_sat(px) : f2i_sat(px * rxf);
+    const int y = kPow2 ? f2i_sat(py) : f2i_sat(py * ryf);
+    const int z = kPow2 ? f2i_sat(pz) : f2i_sat(pz * rzf);
     if ((unsigned)x >= rx || (unsigned)y >= ry || (unsigned)z >= rz) break;
     const unsigned c = (unsigned)(((z >> cs) * my + (y >> cs)) * mx + (x >> cs));
     int d;
@@ -256,7 +270,7 @@ RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
     }
     if (n & 1) { px += delta.x; py += delta.y; pz += delta.z; }
   }
-  p = f3(px, py, pz);
+  p = kPow2 ? f3(px * g_accel.inv_rxf, py * g_accel.inv_ryf, pz * g_accel.inv_rzf) : f3(px, py, pz);
   return found;
 }
 
@@ -271,8 +285,7 @@ RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 de
   const RmOpts& o = g_opts;
   Hit r;
   r.dist = g < 1e5f ? g : 1e5f;
-  r.hit = false;
-  r.closer = false;
+  r.flags = 0;
   r.p = rpos;  // (only read after a hit)
   const bool inside = rpos.x > o.boundsMin.x && rpos.x < o.boundsMax.x && rpos.y > o.boundsMin.y &&
                       rpos.y < o.boundsMax.y && rpos.z > o.boundsMin.z && rpos.z < o.boundsMax.z;
@@ -293,14 +306,14 @@ RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 de
     r.p = p;
     if (found) {
       RM_STAT_EVENT(5);
-      r.hit = true;
+      r.flags = kHit;
       if constexpr (kCount) {
         const int x = f2i_sat(p.x * (float)o.rx), y = f2i_sat(p.y * (float)o.ry), z = f2i_sat(p.z * (float)o.rz);
         c.taps += taps_of_hit(x, y, z, smooth);
       }
       const float3 hp = p * o.voxelBounds2 + (-o.voxelBounds);
       const float d = len3(rpos - hp) - o.voxelSize;
-      if (d < r.dist) { r.dist = d; r.closer = true; }
+      if (d < r.dist) { r.dist = d; r.flags = kHit | kCloser; }
     }
   }
   return r;
@@ -359,12 +372,12 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
   float invS;
   const float3 delta = march_delta(rd, o.maxVoxelIter, invS);
   Hit j;
-  j.dist = 0.0f; j.hit = false; j.closer = false; j.p = f3s(0.0f);
+  j.dist = 0.0f; j.flags = 0; j.p = f3s(0.0f);
   float jg = 0.0f;  // ground distance of the last evaluation (the ground's "id" is (int)g, renderer.cl:211)
   float dist = o.startDist;
   float3 pos = ro;
   const float inv_step = kCount ? 0.0f : 1.01f / len3(delta * o.voxelBounds2);
-  bool cut = false;
+  int cut = 0;
   float tin = -3.0e38f, tout = 3.0e38f;
   if (!kCount) march_window(ro, rd, maxDist, tin, tout);
   while (--maxSteps >= 0) {
@@ -376,9 +389,8 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
     if (!kCount && (dist > tout || tin - dist > g * 1.0001f + 1e-3f || g <= 0.0f)) {
       RM_STAT_EVENT(12);
       j.dist = g < 1e5f ? g : 1e5f;
-      j.hit = false;
-      j.closer = false;
-      cut = false;
+      j.flags = 0;
+      cut = 0;
       if (dist > tout && rd.y >= 0.0f && g > o.eps && g < 1e5f && maxSteps < 65536 &&
           (float)(maxSteps + 1) * g * 0.99f >= maxDist - dist) {
         RM_STAT_EVENT(17);
@@ -391,7 +403,7 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
         float reach = g;
         if (!wantSurface) reach = fminf(reach, fmaxf(maxDist - dist, o.eps));
         const float k = (reach + o.voxelSize) * inv_step;
-        cut = k < (float)(limit - 2);
+        cut = k < (float)(limit - 2) ? 1 : 0;
         if (cut) limit = f2i_sat(k) + 2;
       }
       j = scene_distance<kCount, kMap>(c, pos, rd, delta, limit, invS, g, smooth);
@@ -399,7 +411,7 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
     if (fabsf(j.dist) <= o.eps || dist >= maxDist) break;
     dist += j.dist;
   }
-  if (!kCount && wantSurface && cut && !j.hit) {
+  if (!kCount && wantSurface && cut && !(j.flags & kHit)) {
     RM_STAT_EVENT(10);
     j = scene_distance<kCount, kMap>(c, pos, rd, delta, o.maxVoxelIter, invS, jg, smooth);
   }
@@ -416,14 +428,14 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
   if (!wantSurface) return r;  // shadow rays use the distance only
   const int x = f2i_sat(j.p.x * (float)o.rx), y = f2i_sat(j.p.y * (float)o.ry), z = f2i_sat(j.p.z * (float)o.rz);
   if (!miss) {
-    if (j.closer) {
+    if (j.flags & kCloser) {
       const int v = voxel_value(x, y, z);
       r.objectID = v < 168 ? (v < 84 ? 1 : 2) : 3;  // voxelMaterial, renderer.cl:205-207
     } else {
       r.objectID = f2i_sat(jg < 1e5f ? jg : -1.0f);
     }
   }
-  if (j.hit) r.normal = smooth ? normal_smooth(x, y, z) : normal_6tap(x, y, z);
+  if (j.flags & kHit) r.normal = smooth ? normal_smooth(x, y, z) : normal_6tap(x, y, z);
   else r.normal = jg < 1e5f ? f3(0.0f, 1.0f, 0.0f) : -rd;
   return r;
 }

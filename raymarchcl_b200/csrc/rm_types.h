@@ -82,6 +82,9 @@ struct RmAccel {
   int cell_shift;             // macro-cell edge = 1 << cell_shift voxels (>= 2)
   float cellf;                // (float)(1 << cell_shift)
   float rxf, ryf, rzf;        // (float) of the grid extents: the march multiplies by them at every lookup
+  float inv_rxf, inv_ryf, inv_rzf;  // their reciprocals (exact when the extents are powers of two, see pow2)
+  int pow2;                   // all three extents are powers of two: scaling by them is exact in fp32, so the march's
+                              // recurrence p += delta can run in voxel units (x = trunc(q.x), no multiply per sample)
   const uint8_t* nib;         // the same map packed to 4 bits per cell (min(dist, 15)); cell c = nibble c&1 of byte c>>1.
                               // The default kernel stages it into shared memory with a bulk TMA copy
   unsigned nib_bytes;         // its size, padded to a multiple of 16 bytes (bulk-copy granularity)

@@ -95,6 +95,8 @@ void build_accel(const uint8_t* vox, int rx, int ry, int rz, int iso, int cell_s
   const int cell = 1 << a.cell_shift;
   a.cellf = (float)cell;
   a.rxf = (float)rx; a.ryf = (float)ry; a.rzf = (float)rz;
+  a.inv_rxf = 1.0f / a.rxf; a.inv_ryf = 1.0f / a.ryf; a.inv_rzf = 1.0f / a.rzf;
+  a.pow2 = ((rx & (rx - 1)) == 0 && (ry & (ry - 1)) == 0 && (rz & (rz - 1)) == 0) ? 1 : 0;
   a.mx = (rx + cell - 1) >> a.cell_shift; a.my = (ry + cell - 1) >> a.cell_shift; a.mz = (rz + cell - 1) >> a.cell_shift;
   A.solid.assign((size_t)a.bx * a.by * a.bz, 0);
   A.occ.assign(A.solid.size(), 0);
@@ -200,10 +202,14 @@ void sim_render_pixels(const uint8_t* vox, const float* mc, const void* opts544,
       if (mode == 0) c = plain::render_pixel_sample<false>(s, plain::BrickVolume{}, id);
       else if (mode == 1) c = plain::render_pixel_sample<true>(s, plain::BrickVolume{}, id);
       else if (mode == 2) c = plain::render_pixel_sample<true>(s, plain::ByteVolume{vox}, id);
+      else if (mode == 3 && cell_shift == 2 && fused::g_accel.pow2) c = fused::render_pixel_sample<false, 7>(fused::Cnt<false>{}, lane, id);
+      else if (mode == 3 && fused::g_accel.pow2) c = fused::render_pixel_sample<false, 5>(fused::Cnt<false>{}, lane, id);
       else if (mode == 3 && cell_shift == 2) c = fused::render_pixel_sample<false, 3>(fused::Cnt<false>{}, lane, id);
       else if (mode == 3) c = fused::render_pixel_sample<false, 1>(fused::Cnt<false>{}, lane, id);
       else if (mode == 4 && cell_shift == 2) c = fused::render_pixel_sample<true, 3>(fc, lane, id);
       else if (mode == 4) c = fused::render_pixel_sample<true, 1>(fc, lane, id);
+      else if (mode == 5 && cell_shift == 2 && fused::g_accel.pow2) c = fused::render_pixel_sample<false, 6>(fused::Cnt<false>{}, lane, id);
+      else if (mode == 5 && fused::g_accel.pow2) c = fused::render_pixel_sample<false, 4>(fused::Cnt<false>{}, lane, id);
       else if (mode == 5 && cell_shift == 2) c = fused::render_pixel_sample<false, 2>(fused::Cnt<false>{}, lane, id);
       else if (mode == 5) c = fused::render_pixel_sample<false, 0>(fused::Cnt<false>{}, lane, id);
       else if (cell_shift == 2) c = fused::render_pixel_sample<true, 2>(fc, lane, id);

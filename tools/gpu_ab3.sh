@@ -12,12 +12,9 @@ run() {
 }
 run bricks --kernel bricks
 if [ "${SKIP_AB:-0}" != "1" ]; then
-run b256_k1 --opt 10=256 --opt 12=0 --opt 11=1
-run b256_k1_halves --opt 10=256 --opt 12=0 --opt 11=1 --opt 14=1
-run b256_k2 --opt 10=256 --opt 12=0 --opt 11=2
-run b256_k1_topdown --opt 10=256 --opt 12=0 --opt 11=1 --opt 13=0
-run b1024_k1_halves --opt 10=1024 --opt 12=1 --opt 11=1 --opt 14=1
-run b1024_k0 --opt 10=1024 --opt 12=1 --opt 11=0
+run default
+run b1024_tma --opt 10=1024 --opt 12=1 --opt 11=0
+run b256_free --opt 11=0
 fi
 ncu_cap() {  # block, smem, group
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_persist -s 1 -c 1 -f \
