@@ -44,6 +44,9 @@ WORKLOADS = {
     # reduced copy of c2 for profiling under ncu (kernel replays): quarter frame, 4 passes
     "c2s": dict(name="256^3 gyroid, 960x540, 4 passes, :metal (reduced c2, profiling only)",
                 scene=dict(vres=256, width=960, height=540, iters=4, mat="metal")),
+    # 128^3 copy of c2: its 16 KiB distance map fits the shared memory of every resident block (TMA staging A/B)
+    "g128": dict(name="128^3 gyroid, 1920x1080, 16 passes, :metal (TMA / shared-memory map A/B only)",
+                 scene=dict(vres=128, width=1920, height=1080, iters=16, mat="metal")),
     # the other configs are parity-test cases; selectable here for exploration only
     "c1": dict(name="64^3 gyroid, 256x256, 1 pass, :ao (BASELINE configs[0])",
                scene=dict(vres=64, width=256, height=256, iters=1, mat="ao")),

@@ -70,8 +70,8 @@ typedef struct rm_stats {
 
 typedef enum rm_option {
   RM_OPT_COUNT_WORK = 1,   /* 0 (default) | 1: gather reference-equivalent work counters */
-  RM_OPT_KERNEL = 2,       /* which RenderImage kernel: 0 = default: persistent warps over the bit-brick volume,
-                              distance map staged into shared memory by bulk TMA, blend + tonemap folded in;
+  RM_OPT_KERNEL = 2,       /* which RenderImage kernel: 0 = default: persistent blocks over the bit-brick volume,
+                              blend + tonemap folded in (distance map optionally staged into shared memory by bulk TMA);
                               1 = plain, over the raw byte volume (comparison kernel);
                               2 = warp-scheduled persistent state machine over the bit-brick volume;
                               3 = wavefront pipeline (stages + a persistent, refilling trace kernel);
@@ -87,8 +87,10 @@ typedef enum rm_option {
                               warp are idle (1 = at once ... 32 = the warp starts 32 rays together) */
   RM_OPT_PERSIST_BLOCK = 10, /* kernel 0: resident block layout: 0 = default, 1024 (x 1 block per SM, 64 registers)
                                or 256 (x 5, 48 registers) threads */
-  RM_OPT_PERSIST_SMEM = 12,  /* kernel 0: 1 (default) = stage the 4-bit distance map into shared memory by bulk TMA when a
-                               copy per resident block fits the SM; 0 = always read the byte map from global memory */
+  RM_OPT_PERSIST_SMEM = 12,  /* kernel 0: 1 = stage the 4-bit distance map into shared memory by bulk TMA (cp.async.bulk +
+                               mbarrier) when a copy per resident block fits the SM -- 128 KiB at 256^3, so with the
+                               1024-thread layout only; 0 (default) = read the byte map from global memory / L1, which
+                               measured faster at every volume size */
   RM_OPT_PERSIST_ORDER = 13, /* kernel 0: 1 (default) = walk the frame bottom-up so that the launch ends on the (cheap) top rows; 0 = top-down */
   RM_OPT_PERSIST_HALVES = 14, /* kernel 0, round mode: 1 = the two halves of a block draw and synchronise separately; 0 (default) */
   RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 0 = every warp draws its next work bundle on its own; k >= 1 = the warps of a

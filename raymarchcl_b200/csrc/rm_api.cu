@@ -78,7 +78,8 @@ struct rm_ctx {
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
   int persist_bottom_up = 1;              // RM_OPT_PERSIST_ORDER
   int persist_halves = 0;                 // RM_OPT_PERSIST_HALVES
-  int persist_smem = 1;                   // stage the 4-bit distance map into shared memory when it fits (RM_OPT_PERSIST_SMEM)
+  int persist_smem = 0;                   // 1: stage the 4-bit distance map into shared memory by bulk TMA when it fits (RM_OPT_PERSIST_SMEM);
+                                          // measured slower than the L1-resident byte map at every volume size, hence off
   int persist_group = -1;                 // bundles per warp per block-synchronous round of the default kernel; 0 = free-running; -1 = default
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;

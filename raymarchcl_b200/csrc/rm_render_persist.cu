@@ -65,7 +65,8 @@ __device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
 // Layouts (threads per block x resident blocks per SM), RM_OPT_PERSIST_BLOCK: 1024 x 1 (64 registers,
 // 32 warps per SM, room for a 200 KB distance map) and 256 x 5 (48 registers, 40 warps, <= 40 KB map per
 // block). Every block stages its own copy of the map, so the 128 KiB map of a 256^3 volume only fits
-// the first layout. (640 x 2 at 48 registers was measured too: like 1024 x 1; 128 x 10: 15 % slower.)
+// the first layout. (Measured and dropped, C2 ms per frame against 36.7 for 256 x 5: 640 x 2 at 48 registers
+// 41.2 before the march rewrite, like 1024 x 1; 128 x 10: +15 %; 192 x 6 and 384 x 3 at 56 registers: 38.1 / 38.3.)
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ PersistParams P) {
@@ -197,7 +198,7 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
 }
 
 // function attributes are per device: set once per (device, instantiation)
-std::once_flag g_attr_once[64][32];
+std::once_flag g_attr_once[64][64];
 
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 cudaError_t launch(const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev, cudaStream_t stream) {

@@ -139,7 +139,7 @@ def test_default_kernel_equals_round1_kernel_bit_for_bit(gpu_renderer):
     finally:
         gpu_renderer.set_option(10, 0)
         gpu_renderer.set_option(11, -1)
-        gpu_renderer.set_option(12, 1)
+        gpu_renderer.set_option(12, 0)
 
 
 def test_map_too_large_for_shared_memory_uses_the_global_map(gpu_renderer, oracle):
@@ -155,11 +155,52 @@ def test_map_too_large_for_shared_memory_uses_the_global_map(gpu_renderer, oracl
     ref_px, ref_cnt = oracle.render_frame(vol, mcs, opts, w, h)
     gpu_renderer.set_option(2, 0)
     gpu_renderer.set_option(3, 2)  # force 4-voxel cells
+    gpu_renderer.set_option(12, 1)  # ask for the shared-memory map: it does not fit, the launcher must fall back
     try:
         a, argb_a, cnt = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=True)
         b, argb_b, _ = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=False)
     finally:
         gpu_renderer.set_option(3, 0)
+        gpu_renderer.set_option(12, 0)
     assert np.array_equal(cnt, ref_cnt)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    check_frame(b, ref_px, argb_b, oracle.tonemap(ref_px, opts[0]))
+
+
+@pytest.mark.parametrize("block", [1024, 256], ids=["1024x1", "256x5"])
+@pytest.mark.parametrize("kw", [
+    dict(vres=256, width=320, height=180, iters=16, mat="metal"),                       # C2's volume: 128 KiB of nibbles (1024 x 1 only)
+    dict(vres=128, width=200, height=120, iters=4, mat="metal2", dof=0.025),            # 16 KiB: fits every layout
+    dict(vres=(96, 40, 130), width=120, height=80, iters=3, mat="metal", theta=120.0),  # ragged grid, odd cell count
+    dict(vres=64, width=256, height=256, iters=1, mat="ao"),                            # BASELINE config 1
+], ids=["gyroid256", "gyroid128", "ragged", "c1"])
+def test_distance_map_staged_by_tma_matches_oracle(gpu_renderer, oracle, kw, block):
+    """RM_OPT_PERSIST_SMEM = 1: the 4-bit distance map is copied into shared memory by cp.async.bulk + mbarrier
+    and the march reads it with LDS. Exact counters (the counting kernel reads the staged map too), accumulator
+    and ARGB against the oracle; bit-identical to the default (global byte map) launch."""
+    from raymarchcl_b200 import compute_eyepos, generate_scatter_offsets, make_gyroid_volume, make_render_option_buffers
+    if isinstance(kw["vres"], tuple):
+        vres = kw["vres"]
+        vol = make_gyroid_volume(vres)
+        opts = make_render_option_buffers(kw["iters"], dict(width=kw["width"], height=kw["height"], vres=list(vres), iter=kw["iters"],
+                                                            mat=kw["mat"], eyepos=compute_eyepos(kw["theta"], 2.0, 0.5), targetpos=[0, -0.3, 0]))
+        mcs = [generate_scatter_offsets(0x4000, 5 + i) for i in range(kw["iters"])]
+    else:
+        vol, opts, mcs = build_scene(**kw)
+    w, h = kw["width"], kw["height"]
+    ref_px, ref_cnt = oracle.render_frame(vol, mcs, opts, w, h)
+    r = gpu_renderer
+    r.set_option(2, 0)
+    base, argb_base, _ = render_gpu(r, vol, opts, mcs, w, h, count=False)
+    try:
+        r.set_option(12, 1)
+        r.set_option(10, block)
+        a, argb_a, cnt = render_gpu(r, vol, opts, mcs, w, h, count=True)
+        b, argb_b, _ = render_gpu(r, vol, opts, mcs, w, h, count=False)
+    finally:
+        r.set_option(12, 0)
+        r.set_option(10, 0)
+    assert np.array_equal(cnt, ref_cnt)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(b.view(np.uint32), base.view(np.uint32))
+    assert np.array_equal(argb_b, argb_base)
     check_frame(b, ref_px, argb_b, oracle.tonemap(ref_px, opts[0]))
