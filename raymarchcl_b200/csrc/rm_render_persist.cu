@@ -1,24 +1,28 @@
 // rm_render_persist.cu -- the DEFAULT RenderImage kernel (renderer.cl:478-494) for sm_100a, with
 // the frame's blend (renderer.cl:492) and TonemapImage (renderer.cl:496-508) folded into it.
 //
-//   persistent   one 1024-thread block per SM for the whole launch. Each WARP takes the next bundle
-//                of 32 work items from a global ticket counter when all its lanes are done: no block
-//                ever waits for its slowest warp (the per-item kernel lost 15 % of its warp slots to
-//                that: 52.9 % active of a possible 62.5 %), and because the same threads keep the same
-//                registers there is nothing left in local memory to write back.
+//   persistent   148 x 5 blocks of 256 threads (48 registers, 40 warps per SM) live for the whole launch
+//                and draw work bundles from a global ticket counter -- in block-synchronous rounds: the
+//                8 warps of a block take 8 consecutive bundles and meet at the block barrier before the
+//                next draw. Warps that draw on their own (measured: 38.2 vs 36.7 ms per C2 frame) drift
+//                through the routine independently and stream its 68 KB of code through the 32 KB
+//                instruction cache again and again; the warps of a synchronised block share the lines.
 //   bundles      a bundle is 32 / m neighbouring pixels x the m passes of the launch, pass-minor:
 //                the lanes of a warp render the SAME pixels in different passes (rays that differ
 //                only by jitter), which is what keeps their control flow together.
-//   TMA          on block start one thread arms an mbarrier and issues cp.async.bulk copies of the
-//                4-bit macro-cell distance map (<= 128 KiB at <= 64^3 cells) into shared memory; the
-//                march reads it with LDS (rm_scene_fused.cuh) -- its load from global memory was the
-//                top stall site of the per-item kernel (79 % long-scoreboard).
 //   blend        the m passes of a pixel sit in m adjacent lanes: mix(pixels, colour_k, frameBlend_k)
 //                is folded in pass order with warp shuffles -- the same operations in the same order
 //                as m separate RenderImage launches, hence the same bits -- and written once. No colour
 //                buffer (531 MB at C2), no blend kernel.
 //   tonemap      the lane that writes the accumulator also writes the ARGB word of the frame so far
-//                (gamma of the launch's opts); rm_tonemap returns that buffer when nothing changed.
+//                (gamma of the launch's opts) -- into the context's frame, a caller's gather buffer or,
+//                in a multi-GPU group, straight into GPU 0's frame over NVLink peer memory;
+//                rm_tonemap returns that buffer when nothing changed.
+//   TMA          opt-in (RM_OPT_PERSIST_SMEM): on block start one thread arms an mbarrier and issues
+//                cp.async.bulk copies of the 4-bit macro-cell distance map (128 KiB at 64^3 cells) into
+//                shared memory; the march reads it with LDS (rm_scene_fused.cuh). It removes the map's
+//                long-scoreboard stalls and a third of the L2 traffic and is slower at every volume
+//                size (one 1024-thread block per SM at 256^3; nibble extraction elsewhere): DESIGN.md 4.
 //
 // Compiled with -fmad=false like the rest of the library (pinned two-rounding evaluation order).
 #include <mutex>

@@ -6,14 +6,14 @@
 // shortcuts, irrelevance culling, march windows, early misses; the proofs are written out there and
 // are not repeated here) -- what differs is how the routine sits on the machine:
 //
-//   * every shared (non-inlined) function takes and returns VALUES. nvcc passes them in registers,
-//     so the routine has no call stack at all (ptxas: 0 bytes stack frame); the by-reference
-//     Isec / Scene / JobResult / PixelState of rm_scene_plain.cuh cost 416 bytes of local memory per
-//     thread, ~10 % of the executed instructions and 8.5 GB of DRAM write-backs per C2 frame;
-//   * the distance map is read from SHARED MEMORY: 4 bits per macro-cell (Chebyshev distance
-//     saturated at 15), staged once per resident block with a bulk TMA copy (cp.async.bulk +
-//     mbarrier, rm_render_persist.cu). At <= 64^3 cells that is <= 128 KiB. without kMapNib the routine reads the
-//     byte map from global memory instead (grids whose map does not fit the SM).
+//   * every shared (non-inlined) function takes and returns VALUES, which nvcc passes in registers:
+//     nothing is forced into local memory by having its address taken (the by-reference Isec / Scene /
+//     JobResult / PixelState of rm_scene_plain.cuh were). What remains in local memory is register
+//     spill of the 48-register build;
+//   * the march loop is rewritten for few paths and few instructions (march_fast below);
+//   * the distance map can be read from SHARED MEMORY (kMapNib): 4 bits per macro-cell (Chebyshev
+//     distance saturated at 15), staged once per resident block with a bulk TMA copy (cp.async.bulk +
+//     mbarrier, rm_render_persist.cu). Opt-in: measured slower than the L1-resident byte map.
 //
 // tests/hostsim compiles this header for the host (RM_NIB_BASE is then a plain pointer) and compares
 // the routine with the oracle bit for bit.
