@@ -73,7 +73,14 @@ cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, i
 #define RM_PERSIST_DEFAULT_ROUND 1        // ... drawing bundles in block-synchronous rounds
 // How many of `available` consecutive fusable passes one launch should take: all (<= 32) when they
 // fill >= 80 % of a warp's lanes as whole pixels x passes groups, else the largest power of two.
-int rm_persist_pick_passes(int available);
+inline int rm_persist_pick_passes(int available) {
+  int m = available < RM_MAX_FUSED_PASSES ? available : RM_MAX_FUSED_PASSES;
+  if (m < 1) return 0;
+  if ((32 / m) * m * 5 >= 32 * 4) return m;  // >= 80 % of the lanes carry an item
+  int p = 1;
+  while (p * 2 <= m) p *= 2;
+  return p;
+}
 // RenderImage for `passes` consecutive fusable passes, blended into d_accum in pass order inside the
 // kernel. d_argb (optional): the ARGB words of the frame so far (TonemapImage with opts.gamma), indexed
 // by pixel id or, argb_packed != 0, by shard slot (padding slots = 0). d_queue: one 64-bit ticket

@@ -228,15 +228,6 @@ cudaError_t launch_any(bool count, int threads, const RmShard& shard, const Pers
 
 }  // namespace
 
-int rm_persist_pick_passes(int available) {
-  int m = available < RM_MAX_FUSED_PASSES ? available : RM_MAX_FUSED_PASSES;
-  if (m < 1) return 0;
-  if ((32 / m) * m * 5 >= 32 * 4) return m;  // >= 80 % of the lanes carry an item
-  int p = 1;
-  while (p * 2 <= m) p *= 2;
-  return p;
-}
-
 cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,

@@ -41,6 +41,7 @@ static inline int stat_bucket(int n) {
   return b;
 }
 
+#include "rm_kernels.h"  // rm_slot_to_pixel / rm_shard_layout: the tile ownership the kernels and raymarchcl_b200/dist.py share
 #include "rm_scene_plain.cuh"
 #include "rm_scene_fused.cuh"
 #include "rm_wave.cuh"
@@ -300,6 +301,18 @@ void sim_render_pixels_wave(const uint8_t* vox, const float* mc, const void* opt
 #undef SIM_STAGE
   if (counters) { counters[0] += cs; counters[1] += ct; counters[2] += co; }
 }
+
+// The shard layout exactly as the kernels compute it (rm_types.h:rm_shard_layout, rm_kernels.h:rm_slot_to_pixel):
+// fills out[0 .. slots) with the pixel id of every work slot of `rank` (-1 = padding), returns the slot count.
+long long sim_shard_slots(int W, int H, int rank, int world, int tile_w, int tile_h, int* out, long long cap) {
+  RmShard s{};
+  s.rank = rank; s.world = world; s.tile_w = tile_w; s.tile_h = tile_h;
+  rm_shard_layout(s, W, H);
+  for (long long i = 0; i < s.slots && i < cap; ++i) out[i] = rm_slot_to_pixel(s, i, W, H);
+  return s.slots;
+}
+
+int sim_pick_passes(int available) { return rm_persist_pick_passes(available); }
 
 int sim_stats_words(void) { return (int)(sizeof(SimStats) / 8); }
 void sim_get_stats(unsigned long long* out, int reset) {

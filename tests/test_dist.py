@@ -27,6 +27,30 @@ def test_shards_partition_every_pixel_exactly_once(w, h, world, tw, th):
     assert lay.slots(0) == lay.max_slots  # rank 0 owns the most tiles (rm_shard_slots relies on it)
 
 
+@pytest.mark.parametrize("w,h,world,tw,th", [(1920, 1080, 8, 16, 8), (1920, 1080, 6, 16, 8), (3840, 2160, 8, 16, 8), (100, 70, 5, 16, 8),
+                                             (131, 77, 7, 8, 4), (64, 64, 9, 32, 32), (256, 256, 1, 32, 32)])
+def test_python_shard_layout_is_the_kernels_layout(w, h, world, tw, th):
+    """raymarchcl_b200/dist.py:ShardLayout restates rm_shard_layout / rm_slot_to_pixel (csrc/rm_types.h, rm_kernels.h);
+    tests/hostsim compiles those very headers for the host: slot for slot the same pixel ids, for every rank."""
+    import ctypes as C
+    from tests.hostsim import build_hostsim
+    lib = C.CDLL(build_hostsim.build())
+    lib.sim_shard_slots.restype = C.c_longlong
+    lib.sim_shard_slots.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_longlong]
+    lay = ShardLayout(w, h, world, tw, th)
+    loads = []
+    for r in range(world):
+        want = lay.slot_pixel_index(r)
+        got = np.full(want.size + 8, -7, dtype=np.int32)
+        n = lib.sim_shard_slots(w, h, r, world, tw, th, got.ctypes.data, got.size)
+        assert n == want.size == lay.slots(r)
+        assert np.array_equal(got[:n].astype(np.int64), want)
+        loads.append(int((want >= 0).sum()))
+    assert sum(loads) == w * h
+    if world > 1 and w * h > 100000:
+        assert max(loads) / (sum(loads) / world) < 1.02  # diagonal stripes deal the pixels evenly
+
+
 def test_warp_bundles_are_8x4_pixel_blocks():
     lay = ShardLayout(64, 64, 2, 32, 32)
     idx = lay.slot_pixel_index(1)[:32]

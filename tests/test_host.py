@@ -141,3 +141,22 @@ def test_product_code_never_touches_the_oracle():
                 if re.search(r"(from|import)\s+oracle|oracle/|librm_oracle|libref_", txt):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_pass_chunking_of_the_default_kernel():
+    """rm_persist_pick_passes (csrc/rm_kernels.h, compiled for the host by tests/hostsim): a frame's passes are cut
+    into launches of m <= 32 whose bundles (32 // m pixels x m passes) fill >= 80 % of a warp, else a power of two."""
+    import ctypes as C
+    from tests.hostsim import build_hostsim
+    lib = C.CDLL(build_hostsim.build())
+    lib.sim_pick_passes.argtypes = [C.c_int]
+    for n in range(1, 201):
+        left, chunks = n, []
+        while left:
+            m = lib.sim_pick_passes(left)
+            assert 1 <= m <= min(left, 32)
+            assert (32 // m) * m >= 26 or (m & (m - 1)) == 0, (n, m)
+            chunks.append(m)
+            left -= m
+        assert sum(chunks) == n
+    assert [lib.sim_pick_passes(k) for k in (16, 100, 11, 17, 3, 33)] == [16, 32, 8, 16, 3, 32]
