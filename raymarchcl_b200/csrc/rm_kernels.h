@@ -6,20 +6,28 @@
 // tiles row by row); inside a tile consecutive groups of 32 slots cover 8x4 pixel blocks so that a
 // warp traces a compact bundle of primary rays.
 __host__ __device__ inline int rm_slot_to_pixel(const RmShard& sh, long long slot, int W, int H) {
-  const int tile_px = sh.tile_w * sh.tile_h;
-  const long long lt = slot / tile_px;
-  const int r = (int)(slot - lt * tile_px);
-  const int ty = (int)(lt / sh.tiles_per_rank_row), k = (int)(lt - (long long)ty * sh.tiles_per_rank_row);
+  const unsigned tile_px = (unsigned)(sh.tile_w * sh.tile_h);
+  unsigned lt, r;
+  if (slot < 0x7fffffffLL) {  // every frame up to 2^31 slots: 32-bit divisions (a 64-bit one is ~100 instructions)
+    const unsigned s32 = (unsigned)slot;
+    lt = s32 / tile_px;
+    r = s32 - lt * tile_px;
+  } else {
+    const long long l64 = slot / tile_px;
+    lt = (unsigned)l64;
+    r = (unsigned)(slot - l64 * tile_px);
+  }
+  const unsigned ty = lt / (unsigned)sh.tiles_per_rank_row, k = lt - ty * (unsigned)sh.tiles_per_rank_row;
   // the rank's first column in this tile row: (tx + skew * ty) mod world == rank
-  int first = (sh.rank - (int)(((long long)sh.skew * ty) % sh.world)) % sh.world;
+  int first = (sh.rank - (int)(((unsigned)sh.skew * ty) % (unsigned)sh.world)) % sh.world;
   if (first < 0) first += sh.world;
-  const int tx = first + k * sh.world;
+  const int tx = first + (int)k * sh.world;
   if (tx >= sh.tiles_x) return -1;
-  const int sb = r >> 5, l = r & 31;
-  const int sbw = sh.tile_w >> 3;
-  const int sby = sb / sbw, sbx = sb - sby * sbw;
-  const int x = tx * sh.tile_w + sbx * 8 + (l & 7);
-  const int y = ty * sh.tile_h + sby * 4 + (l >> 3);
+  const unsigned sb = r >> 5, l = r & 31u;
+  const unsigned sbw = (unsigned)sh.tile_w >> 3;
+  const unsigned sby = sb / sbw, sbx = sb - sby * sbw;
+  const int x = tx * sh.tile_w + (int)(sbx * 8u + (l & 7u));
+  const int y = (int)ty * sh.tile_h + (int)(sby * 4u + (l >> 3));
   if (x >= W || y >= H) return -1;
   return y * W + x;
 }
