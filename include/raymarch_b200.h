@@ -121,7 +121,8 @@ const char* rm_last_error(const rm_ctx* ctx);
 /* v-buf upload (vio/load-volume, io.clj:19-33 + {:write [.. v-buf]}, core.clj:81). */
 int rm_set_volume(rm_ctx* ctx, const uint8_t* voxels, int rx, int ry, int rz);
 /* The same from DEVICE memory (a volume assembled over NVLink or written by another kernel): one
- * device-to-device copy on the context's stream. */
+ * device-to-device copy, queued on the context's stream -- the source must stay valid (and unchanged) until
+ * that copy has run: rm_sync, or any later blocking call of this context. */
 int rm_set_volume_device(rm_ctx* ctx, const void* d_voxels, int rx, int ry, int rz);
 /* The same from a .vox file as vio/save-volume writes it (io.clj:9-17: "VOXEL", 3 x int32 big-endian,
  * element-size byte, raw bytes): reads through pinned memory and uploads. The extents are returned

@@ -11,12 +11,9 @@ run() {
   echo "$name: $(python -c "import json;d=json.load(open('gpurun_out/${TAG}_${name}.json'));print(round(d['ms_per_step'],3), round(d['roofline']['kernel_ms_per_frame'],3))" 2>&1 | tail -1)"
 }
 if [ "${SKIP_AB:-0}" != "1" ]; then
+run bricks --kernel bricks
 run default
-run g128_smem --workload g128 --opt 12=1
-run g128_glob --workload g128 --opt 12=0
-run g128_1024_smem --workload g128 --opt 10=1024 --opt 11=0 --opt 12=1
-run c1_smem --workload c1 --opt 12=1
-run c1_glob --workload c1 --opt 12=0
+run default_again
 fi
 ncu_cap() {  # block, smem, group
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_persist -s 1 -c 1 -f \
