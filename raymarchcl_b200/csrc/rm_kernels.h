@@ -7,16 +7,11 @@
 // warp traces a compact bundle of primary rays.
 __host__ __device__ inline int rm_slot_to_pixel(const RmShard& sh, long long slot, int W, int H) {
   const unsigned tile_px = (unsigned)(sh.tile_w * sh.tile_h);
-  unsigned lt, r;
-  if (slot < 0x7fffffffLL) {  // every frame up to 2^31 slots: 32-bit divisions (a 64-bit one is ~100 instructions)
-    const unsigned s32 = (unsigned)slot;
-    lt = s32 / tile_px;
-    r = s32 - lt * tile_px;
-  } else {
-    const long long l64 = slot / tile_px;
-    lt = (unsigned)l64;
-    r = (unsigned)(slot - l64 * tile_px);
-  }
+  // 32-bit divisions (a 64-bit one is ~100 instructions): rm_clear_accum bounds the frame to 2^31 / 37 pixels,
+  // so a shard's slots -- pixels plus the padding of edge tiles and columns -- stay far below 2^32
+  const unsigned s32 = (unsigned)slot;
+  const unsigned lt = s32 / tile_px;
+  const unsigned r = s32 - lt * tile_px;
   const unsigned ty = lt / (unsigned)sh.tiles_per_rank_row, k = lt - ty * (unsigned)sh.tiles_per_rank_row;
   // the rank's first column in this tile row: (tx + skew * ty) mod world == rank
   int first = (sh.rank - (int)(((unsigned)sh.skew * ty) % (unsigned)sh.world)) % sh.world;

@@ -179,9 +179,9 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
     }
     if (in_shard && pass == 0) {
       if (id >= 0) P.accum[id] = make_float4(p.x, p.y, p.z, 1.0f);
-      if (P.argb) {
-        if (P.argb_packed) P.argb[slot] = id >= 0 ? tonemap_pack3(p, P.gamma) : 0u;
-        else if (id >= 0) P.argb[id] = tonemap_pack3(p, P.gamma);
+      if (P.argb && (id >= 0 || P.argb_packed)) {
+        const uint32_t word = id >= 0 ? tonemap_pack3(p, P.gamma) : 0u;  // (padding slots of a packed shard read 0)
+        P.argb[P.argb_packed ? slot : (long long)id] = word;
       }
     }
   }

@@ -99,8 +99,9 @@ RM_DEV float3 table_xyz(const Lane& s, uint32_t seed) {
   return f3(t.x, t.y, t.z);
 }
 
-// renderer.cl:153-161
-RM_DEV float box_entry(float3 bmin, float3 bmax, float3 p, float3 d) {
+// renderer.cl:153-161. Shared and out of line: six IEEE divisions (~100 instructions) that the inside / away
+// shortcuts of scene_distance make rare -- kept out of that function's hot body.
+RM_SHARED_FN float box_entry(float3 bmin, float3 bmax, float3 p, float3 d) {
   const float3 t0 = (bmin - p) / d;
   const float3 t1 = (bmax - p) / d;
   const float a = cl_max(cl_max(cl_min(t1.x, t0.x), 0.0f), cl_max(cl_min(t1.y, t0.y), cl_min(t1.z, t0.z)));
@@ -155,17 +156,47 @@ RM_DEV float3 normal_6tap(int x, int y, int z) {
   gradient6_i(x, y, z, gx, gy, gz);
   return unit3(f3(-(float)(-gx), -(float)(-gy), -(float)(-gz)));
 }
-// voxelNormalSmooth (renderer.cl:190-203); the reference's float sums of 0 / +-1 are exact
+// Five occupancy bits of the voxels (x0 .. x0+4, Y, Z), bit i = voxel x0 + i; 0 outside the grid. The five
+// voxels always straddle exactly two bricks of the row.
+RM_DEV unsigned occ_row5(int x0, int Y, int Z) {
+  if ((unsigned)Y >= (unsigned)g_opts.ry || (unsigned)Z >= (unsigned)g_opts.rz) return 0u;
+  const int bxi = x0 >> 2;  // (x0 >= -2: an arithmetic shift gives brick -1 for x0 < 0)
+  const unsigned row = (unsigned)(((Z >> 2) * g_accel.by + (Y >> 2)) * g_accel.bx);
+  const unsigned nyb = (unsigned)(((Y & 3) << 2) | ((Z & 3) << 4));  // where the x-row sits inside a brick word
+  unsigned lo = 0u, hi = 0u;
+  if ((unsigned)bxi < (unsigned)g_accel.bx) lo = (unsigned)(__ldg(g_accel.occ + row + (unsigned)bxi) >> nyb) & 15u;
+  if ((unsigned)(bxi + 1) < (unsigned)g_accel.bx) hi = (unsigned)(__ldg(g_accel.occ + row + (unsigned)(bxi + 1)) >> nyb) & 15u;
+  return ((lo | (hi << 4)) >> (x0 & 3)) & 31u;
+}
+
+// voxelNormalSmooth (renderer.cl:190-203). The reference sums, over the occupied voxels q + d of the 3x3x3
+// neighbourhood, their 6-tap gradients (occ(q+d-e) - occ(q+d+e) per axis e): <= 27 + 162 taps. The sums are sums
+// of 0 / +-1, hence exact integers in any order, and along one axis they telescope: with a_k = occ(q + k*e + rest),
+//   sum_{k=-1..1} a_k (a_{k-1} - a_{k+1}) = a_{-2} a_{-1} - a_1 a_2,
+// so each component is a difference of two population counts over 9 rows: 21 five-voxel rows (42 brick words)
+// instead of up to 189 single-voxel lookups, and the same integers.
 RM_DEV float3 normal_smooth(int x, int y, int z) {
   int sx = 0, sy = 0, sz = 0;
-  for (int dz = -1; dz <= 1; ++dz)
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx)
-        if (occ_at(x + dx, y + dy, z + dz)) {
-          int gx, gy, gz;
-          gradient6_i(x + dx, y + dy, z + dz, gx, gy, gz);
-          sx += gx; sy += gy; sz += gz;
-        }
+  unsigned zprev = 0u;  // rows (dy = -1, 0, 1) of the previous z-slice, 5 bits each
+#pragma unroll 1
+  for (int dz = -2; dz <= 2; ++dz) {
+    const bool zin = dz >= -1 && dz <= 1;
+    unsigned zcur = 0u, yprev = 0u;
+#pragma unroll 1
+    for (int dy = zin ? -2 : -1; dy <= (zin ? 2 : 1); ++dy) {
+      const unsigned r = occ_row5(x - 2, y + dy, z + dz);
+      if (zin) {
+        if (dy == -1) sy += __popc(yprev & r & 14u);  // rows y-2, y-1
+        if (dy == 2) sy -= __popc(yprev & r & 14u);   // rows y+1, y+2
+        if (dy >= -1 && dy <= 1) sx += (int)((r & (r >> 1)) & 1u) - (int)(((r >> 3) & (r >> 4)) & 1u);
+      }
+      if (dy >= -1 && dy <= 1) zcur |= r << (5 * (dy + 1));
+      yprev = r;
+    }
+    if (dz == -1) sz += __popc(zprev & zcur & 0x39ceu);  // slices z-2, z-1 (mask: x offsets -1..1 of the three rows)
+    if (dz == 2) sz -= __popc(zprev & zcur & 0x39ceu);   // slices z+1, z+2
+    zprev = zcur;
+  }
   return unit3(f3((float)sx, (float)sy, (float)sz));
 }
 // reference-equivalent occupancy taps of one hit (counting kernels only)

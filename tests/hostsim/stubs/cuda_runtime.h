@@ -32,6 +32,7 @@ static inline int __float2int_rz(float f) {
   return (int)f;
 }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
