@@ -179,6 +179,7 @@ void decode_opts(const void* blob, RmOpts* o) {
     o->mat[i].r0 = rd_f(b, 416 + 32 * i + 16);
     o->mat[i].smoothness = rd_f(b, 416 + 32 * i + 20);
   }
+  rm_derive_opts(o);
 }
 
 int check_opts(rm_ctx* ctx, const RmOpts& o) {

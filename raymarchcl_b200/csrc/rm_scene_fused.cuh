@@ -539,7 +539,9 @@ RM_DEV float ambient_occlusion(RM_CNT c, Lane s, float3 pos, float3 n0) {
       const float3 delta = march_delta(n, msteps, invS);
       int limit = msteps;
       if (!kCount && o.aoAmp >= 0.0f && d > 0.0f) {
-        const float k = (d + o.voxelSize) * 1.01f / len3(delta * o.voxelBounds2);
+        // (n is a unit vector -- or 0, and then the march does not move and its length is immaterial --, so the
+        //  samples within the reach are bounded by a per-launch constant: no sqrt, no division per probe)
+        const float k = (d + o.voxelSize) * o.ao_k;
         if (k < (float)msteps) limit = f2i_sat(k) + 2 < msteps ? f2i_sat(k) + 2 : msteps;
       }
       RM_STAT_EVENT(11);

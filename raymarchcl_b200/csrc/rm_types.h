@@ -27,7 +27,23 @@ struct RmOpts {
   int isoVal, numLights;
   float3 lightPos[4], lightColor[4];
   RmMaterial mat[4];
+  // derived by rm_derive_opts (not part of the 544-byte blob)
+  float ao_k;  // AO probes: samples per world unit of reach, a conservative upper bound (rm_scene_fused.cuh:ambient_occlusion)
 };
+
+// Derived constants of a decoded TRenderOpts; called by every decoder (rm_api.cu, tests/hostsim).
+inline void rm_derive_opts(RmOpts* o) {
+  // An AO probe marches along a UNIT direction n with delta = (n / (msteps * 0.5)) * invVoxelScale, i.e. world steps of
+  // |n (.) invVoxelScale (.) voxelBounds2| / (msteps * 0.5) >= 0.999 * min_i |invVoxelScale_i * voxelBounds2_i| / (msteps * 0.5)
+  // (0.999 covers |n| = 1 +- 1e-6 and the rounding of delta): the number of samples within a reach r is at most r * ao_k.
+  const float fx = o->invVoxelScale.x * o->voxelBounds2.x, fy = o->invVoxelScale.y * o->voxelBounds2.y, fz = o->invVoxelScale.z * o->voxelBounds2.z;
+  float m = fx < 0.f ? -fx : fx;
+  const float ay = fy < 0.f ? -fy : fy, az = fz < 0.f ? -fz : fz;
+  m = ay < m ? ay : m;
+  m = az < m ? az : m;
+  const float c = (float)(o->maxVoxelIter / 2) * 0.5f;
+  o->ao_k = (m > 1e-20f && m < 1e20f && c > 0.f) ? 1.01f * c / (0.999f * m) : 3.0e38f;  // (3e38: never cut)
+}
 
 // Interleaved tile ownership: the frame is cut into tile_w x tile_h pixel tiles and tile
 // (i, j) belongs to rank (i + skew * j) mod world -- diagonal stripes. (Round 1 dealt tiles row-major,

@@ -79,6 +79,7 @@ void decode_opts(const void* blob, RmOpts* o) {
     o->mat[i].r0 = rd_f(b, 416 + 32 * i + 16);
     o->mat[i].smoothness = rd_f(b, 416 + 32 * i + 20);
   }
+  rm_derive_opts(o);
 }
 
 // CPU restatement of rm_accel.cu
