@@ -320,12 +320,17 @@ RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 de
   r.p = rpos;  // (only read after a hit)
   const bool inside = rpos.x > o.boundsMin.x && rpos.x < o.boundsMax.x && rpos.y > o.boundsMin.y &&
                       rpos.y < o.boundsMax.y && rpos.z > o.boundsMin.z && rpos.z < o.boundsMax.z;
-  const bool away = (rpos.x > o.boundsMax.x && dir.x > 0.0f) || (rpos.x < o.boundsMin.x && dir.x < 0.0f) ||
-                    (rpos.y > o.boundsMax.y && dir.y > 0.0f) || (rpos.y < o.boundsMin.y && dir.y < 0.0f) ||
-                    (rpos.z > o.boundsMax.z && dir.z > 0.0f) || (rpos.z < o.boundsMin.z && dir.z < 0.0f);
-  const float idist = inside ? 0.0f : (away ? -1.0f : box_entry(o.boundsMin, o.boundsMax, rpos, dir));
+  float idist = 0.0f;
   RM_STAT_EVENT(0);
-  RM_STAT_EVENT(inside ? 1 : (away ? 2 : 3));
+  if (!inside) {  // (a real branch: the call sites that reach this function are mostly inside the box already)
+    const bool away = (rpos.x > o.boundsMax.x && dir.x > 0.0f) || (rpos.x < o.boundsMin.x && dir.x < 0.0f) ||
+                      (rpos.y > o.boundsMax.y && dir.y > 0.0f) || (rpos.y < o.boundsMin.y && dir.y < 0.0f) ||
+                      (rpos.z > o.boundsMax.z && dir.z > 0.0f) || (rpos.z < o.boundsMin.z && dir.z < 0.0f);
+    idist = away ? -1.0f : box_entry(o.boundsMin, o.boundsMax, rpos, dir);
+    RM_STAT_EVENT(away ? 2 : 3);
+  } else {
+    RM_STAT_EVENT(1);
+  }
   if (idist >= 0.0f && idist < r.dist) {
     RM_STAT_EVENT(4);
     float3 p = rpos + o.voxelBounds;
@@ -367,10 +372,10 @@ RM_DEV void march_window(float3 ro, float3 rd, float maxDist, float& tin, float&
   tout = kInf;
   const float ro_[3] = {ro.x, ro.y, ro.z}, rd_[3] = {rd.x, rd.y, rd.z};
   const float lo_[3] = {o.boundsMin.x, o.boundsMin.y, o.boundsMin.z}, hi_[3] = {o.boundsMax.x, o.boundsMax.y, o.boundsMax.z};
-  bool ok = maxDist <= kBig, miss = false;
+  // (the box itself is checked once per launch: o.window_ok, rm_derive_opts)
+  bool ok = o.window_ok && maxDist <= kBig, miss = false;
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-    ok = ok && fabsf(ro_[i]) <= kBig && fabsf(lo_[i]) <= kBig && fabsf(hi_[i]) <= kBig && fabsf(rd_[i]) <= 2.0f;
+  for (int i = 0; i < 3; ++i) ok = ok && fabsf(ro_[i]) <= kBig && fabsf(rd_[i]) <= 2.0f;
   if (!ok) return;
   float a = -kInf, b = kInf;
 #pragma unroll
@@ -396,7 +401,7 @@ RM_DEV void march_window(float3 ro, float3 rd, float maxDist, float& tin, float&
 #endif
 template <bool kCount, int kMap>
 RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist, int maxSteps, bool smooth,
-                                   bool wantSurface) {
+                                   bool wantSurface, bool unitDir) {
   const RmOpts& o = g_opts;
   RM_STAT_TRACE();
   RM_STAT_EVENT(wantSurface ? 6 : 7);
@@ -407,7 +412,9 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
   float jg = 0.0f;  // ground distance of the last evaluation (the ground's "id" is (int)g, renderer.cl:211)
   float dist = o.startDist;
   float3 pos = ro;
-  const float inv_step = kCount ? 0.0f : 1.01f / len3(delta * o.voxelBounds2);
+  // samples per world unit along the ray, a conservative upper bound (only used to cut marches short): for a unit
+  // direction the per-launch constant of rm_derive_opts, else from the step's length
+  const float inv_step = kCount ? 0.0f : (unitDir ? o.st_k : 1.01f / len3(delta * o.voxelBounds2));
   int cut = 0;
   float tin = -3.0e38f, tout = 3.0e38f;
   if (!kCount) march_window(ro, rd, maxDist, tin, tout);
@@ -580,7 +587,7 @@ RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float px, float py, fl
       const bool irrelevant = !kCount && kd == 0.0f && ks == 0.0f && zero.x == 0.0f && zero.y == 0.0f && zero.z == 0.0f;
       if (!irrelevant) {
         RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16 + 1 + i);
-        const Isec sh = sphere_trace<kCount, kMap>(c, ipos + ldir * o.shadowBias, ldir, lmax, o.shadowIter, false, false);
+        const Isec sh = sphere_trace<kCount, kMap>(c, ipos + ldir * o.shadowBias, ldir, lmax, o.shadowIter, false, false, true);
         const float sf = sh.distance < lmax ? 0.0f : 1.0f;
         if (sf > 0.0f) {
           diff = diff + inc * kd;
@@ -602,7 +609,7 @@ RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal,
   const RmOpts& o = g_opts;
   RM_STAT_LEVEL(0);
   RM_STAT_SITE(0);
-  const Isec isec = sphere_trace<kCount, kMap>(c, ro, rd, o.maxDist, o.maxIter, true, true);
+  const Isec isec = sphere_trace<kCount, kMap>(c, ro, rd, o.maxDist, o.maxIter, true, true, true);
   float3 col;
   if (isec.distance >= o.maxDist) {
     col = sky(rd);
@@ -618,7 +625,7 @@ RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal,
         const float3 bo = bpos + bd * 0.0075f;
         RM_STAT_LEVEL(i + 1);
         RM_STAT_SITE(RM_STAT_LEVEL_GET() * 16);
-        const Isec ri = sphere_trace<kCount, kMap>(c, bo, bd, o.maxDist, o.maxIter, false, true);
+        const Isec ri = sphere_trace<kCount, kMap>(c, bo, bd, o.maxDist, o.maxIter, false, true, false);  // (a reflection about an un-normalised normal is not a unit vector)
         float3 bc;
         if (ri.objectID < 0) bc = sky(bd);
         else bc = object_lighting<kCount, kMap>(c, s, px, py, bd, ri.pos, mat_index(ri.objectID), ri.normal,

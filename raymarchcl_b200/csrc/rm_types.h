@@ -29,6 +29,8 @@ struct RmOpts {
   RmMaterial mat[4];
   // derived by rm_derive_opts (not part of the 544-byte blob)
   float ao_k;  // AO probes: samples per world unit of reach, a conservative upper bound (rm_scene_fused.cuh:ambient_occlusion)
+  float st_k;  // the same for sphere traces along a unit direction (maxVoxelIter steps)
+  int window_ok;  // the voxel box is small enough for march_window's error bounds (|bounds| <= 64)
 };
 
 // Derived constants of a decoded TRenderOpts; called by every decoder (rm_api.cu, tests/hostsim).
@@ -43,6 +45,12 @@ inline void rm_derive_opts(RmOpts* o) {
   m = az < m ? az : m;
   const float c = (float)(o->maxVoxelIter / 2) * 0.5f;
   o->ao_k = (m > 1e-20f && m < 1e20f && c > 0.f) ? 1.01f * c / (0.999f * m) : 3.0e38f;  // (3e38: never cut)
+  const float c2 = (float)o->maxVoxelIter * 0.5f;
+  o->st_k = (m > 1e-20f && m < 1e20f && c2 > 0.f) ? 1.01f * c2 / (0.999f * m) : 3.0e38f;
+  const float b6[6] = {o->boundsMin.x, o->boundsMin.y, o->boundsMin.z, o->boundsMax.x, o->boundsMax.y, o->boundsMax.z};
+  o->window_ok = 1;
+  for (int i = 0; i < 6; ++i)
+    if (!((b6[i] < 0.f ? -b6[i] : b6[i]) <= 64.0f)) o->window_ok = 0;  // (NaN fails too)
 }
 
 // Interleaved tile ownership: the frame is cut into tile_w x tile_h pixel tiles and tile
