@@ -92,9 +92,8 @@ typedef enum rm_option {
                                1024-thread layout only; 0 (default) = read the byte map from global memory / L1, which
                                measured faster at every volume size */
   RM_OPT_PERSIST_ORDER = 13, /* kernel 0: 1 (default) = walk the frame bottom-up so that the launch ends on the (cheap) top rows; 0 = top-down */
-  RM_OPT_PERSIST_HALVES = 14, /* kernel 0, round mode: 1 = the two halves of a block draw and synchronise separately; 0 (default) */
-  RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 0 = every warp draws its next work bundle on its own; k >= 1 = the warps of a
-                               block draw k bundles each together and meet at the block barrier per draw; -1 = default */
+  RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 0 = every warp draws its next work bundle on its own; 1 = the warps of a block draw
+                               one bundle each together and meet at the block barrier per draw; -1 = default (1) */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */

@@ -28,7 +28,6 @@ RM_OPT_PERSIST_BLOCK = 10
 RM_OPT_PERSIST_GROUP = 11
 RM_OPT_PERSIST_SMEM = 12
 RM_OPT_PERSIST_ORDER = 13
-RM_OPT_PERSIST_HALVES = 14
 
 # every symbol include/raymarch_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [

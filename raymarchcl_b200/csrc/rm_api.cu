@@ -77,10 +77,9 @@ struct rm_ctx {
   unsigned long long* d_queue = nullptr;  // [0] work queue head of the warp kernel, [1] bundle tickets of the default kernel
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
   int persist_bottom_up = 1;              // RM_OPT_PERSIST_ORDER
-  int persist_halves = 0;                 // RM_OPT_PERSIST_HALVES
   int persist_smem = 0;                   // 1: stage the 4-bit distance map into shared memory by bulk TMA when it fits (RM_OPT_PERSIST_SMEM);
                                           // measured slower than the L1-resident byte map at every volume size, hence off
-  int persist_group = -1;                 // bundles per warp per block-synchronous round of the default kernel; 0 = free-running; -1 = default
+  int persist_group = -1;                 // 1 = block-synchronous rounds of the default kernel; 0 = free-running warps; -1 = default
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
   int warp_blocks[2] = {0, 0};            // resident blocks per SM of the warp kernel [plain, counting]
@@ -390,7 +389,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
           const int persist_block = c->persist_block ? c->persist_block : RM_PERSIST_DEFAULT_BLOCK;
           const int persist_group = c->persist_group >= 0 ? c->persist_group : RM_PERSIST_DEFAULT_ROUND;
           e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
-                                       argb, packed, cnt, c->d_queue + 1, c->num_sms, persist_block, persist_group, c->persist_smem, c->persist_bottom_up, c->persist_halves, c->stream);
+                                       argb, packed, cnt, c->d_queue + 1, c->num_sms, persist_block, persist_group, c->persist_smem, c->persist_bottom_up, c->stream);
           launched = 1;
           if (e == cudaSuccess && argb) {
             c->argb_fresh_ptr = argb;
@@ -1153,9 +1152,6 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
         return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_BLOCK: 0 (default), 1024 (x 1 block per SM) or 256 (x 5) threads");
       c->persist_block = (int)value;
       return RM_OK;
-    case RM_OPT_PERSIST_HALVES:
-      c->persist_halves = value != 0;
-      return RM_OK;
     case RM_OPT_PERSIST_ORDER:
       c->persist_bottom_up = value != 0;
       return RM_OK;
@@ -1163,7 +1159,7 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
       c->persist_smem = value != 0;
       return RM_OK;
     case RM_OPT_PERSIST_GROUP:
-      if (value < -1 || value > 64) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_GROUP: -1 (default), 0 (free-running warps) or 1..64 bundles per warp per round");
+      if (value < -1 || value > 1) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_GROUP: -1 (default), 0 (free-running warps) or 1 (block-synchronous rounds)");
       c->persist_group = (int)value;
       return RM_OK;
     case RM_OPT_FUSE_LIMIT:

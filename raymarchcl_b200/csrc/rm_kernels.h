@@ -91,12 +91,12 @@ inline int rm_persist_pick_passes(int available) {
 // block_threads: layout of the resident blocks: 1024 (x 1 per SM, 64 registers) or 256 (x 5 per SM, 48 registers).
 // smem_map: 0 = read the distance map from global memory even when the 4-bit copy would fit the SM's shared memory.
 // bottom_up: hand the bundles out from the end of the slot list (the launch ends on the image's top rows).
-// round_bundles: 0 = free-running warps; k = the block draws warps x k bundles together and meets at its barrier per draw.
+// round_bundles: 0 = free-running warps; else the block draws one bundle per warp together and meets at its barrier per draw.
 cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, int num_sms,
-                                     int block_threads, int round_bundles, int smem_map, int bottom_up, int half_groups, cudaStream_t stream);
+                                     int block_threads, int round_bundles, int smem_map, int bottom_up, cudaStream_t stream);
 
 // ---- warp-scheduled state machine (rm_render_warp.cu), RM_OPT_KERNEL = 2 ----
 int rm_warp_blocks_per_sm(int count);

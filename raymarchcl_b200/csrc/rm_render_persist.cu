@@ -48,9 +48,8 @@ struct PersistParams {
   int ppb;                           // pixels per bundle = 32 / m
   const uint8_t* nib;                // 4-bit distance map in global memory (source of the bulk copy)
   unsigned nib_bytes;                // multiple of 16
-  int round_bundles;                 // 0 = free-running warps; k = block-synchronous rounds of k bundles per warp
+  int round_bundles;                 // 0 = free-running warps; else block-synchronous rounds of one bundle per warp
   int bottom_up;                     // hand the bundles out last-to-first
-  int half_groups;                   // round mode: the two halves of a block draw / synchronise separately
 };
 
 // tonemap + pack of one pixel (renderer.cl:448-454, :502-506); same expression as rm_kernels.cu
@@ -115,44 +114,32 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
   // Scheduling granularity (round_bundles, RM_OPT_PERSIST_GROUP).
   //   0: every warp draws its next bundle on its own -- no warp ever waits for another, but the warps of
   //      an SM drift through the routine independently and the kernel's code (2x the 32 KB L1.5 instruction
-  //      cache, ~40 KB of it touched once per bundle) is fetched again and again: ncu stall_no_instruction
-  //      2.2 - 3.0 per issue.
-  //   k: the block draws (its warps) x k consecutive bundles together, warp w takes bundles w, w + W, ...
-  //      and the block meets at its barrier before the next draw. Its warps then run the same phases of
-  //      the routine at about the same time and share the instruction lines they pull in (stall_no_instruction
-  //      0.9), at the price of waiting for the slowest warp of a round; larger k = fewer, relatively
-  //      shorter waits but more drift.
-  __shared__ unsigned long long s_ticket[2][2];
-  const int K = P.round_bundles;
-  // half_groups: the two halves of the block (warps 0..W/2-1 and W/2..W-1) draw and synchronise separately,
-  // over named barriers 1 and 2 (constant ids: ptxas reserves 3 barriers, not 16)
-  const bool halves = P.half_groups != 0 && kThreads >= 128;
-  const int W = halves ? kThreads / 64 : kThreads / 32;
-  const int warp_all = (int)(threadIdx.x >> 5);
-  const int half = halves && warp_all >= W ? 1 : 0;
-  const int warp = warp_all - half * W;
+  //      cache, most of it touched once per bundle) is fetched again and again: ncu stall_no_instruction
+  //      3.5 per issue.
+  //   1: the block draws one bundle per warp together (warp w takes bundle t0 + w) and meets at its barrier
+  //      before the next draw. Its warps then run the same phases of the routine at about the same time and
+  //      share the instruction lines they pull in (stall_no_instruction 0.9), at the price of waiting for the
+  //      slowest warp of a round (17 % of the warp-time) -- and still 4 % faster.
+  //   (Measured and removed: 2 / 4 bundles per warp per round, two half-block sync groups over named barriers,
+  //    named-barrier groups inside a 1024-thread block: all slower, profiles/r02_scheduling_ab.md.)
+  __shared__ unsigned long long s_ticket[2];
+  const bool rounds = P.round_bundles != 0;
+  constexpr int W = kThreads / 32;
+  const int warp = (int)(threadIdx.x >> 5);
   unsigned round = 0;
-  unsigned long long t0 = 0;
-  int in_round = K;
   for (;;) {
     unsigned long long t = 0;
-    if (K == 0) {
+    if (!rounds) {
       if (lane == 0) t = atomicAdd(P.queue, 1ull);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= (unsigned long long)P.bundles) break;
     } else {
-      if (in_round == K) {
-        if (warp == 0 && lane == 0) s_ticket[half][round & 1u] = atomicAdd(P.queue, (unsigned long long)(W * K));
-        if (!halves) __syncthreads();
-        else if (half == 0) asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
-        else asm volatile("bar.sync 2, %0;" ::"r"(W * 32) : "memory");
-        t0 = s_ticket[half][round & 1u];
-        ++round;
-        in_round = 0;
-        if (t0 >= (unsigned long long)P.bundles) break;  // the whole group leaves together
-      }
-      t = t0 + (unsigned)(warp + W * in_round);
-      ++in_round;
+      if (threadIdx.x == 0) s_ticket[round & 1u] = atomicAdd(P.queue, (unsigned long long)W);
+      __syncthreads();
+      const unsigned long long t0 = s_ticket[round & 1u];
+      ++round;
+      if (t0 >= (unsigned long long)P.bundles) break;  // the whole block leaves together
+      t = t0 + (unsigned)warp;
       if (t >= (unsigned long long)P.bundles) continue;  // ragged last draw: sit this one out
     }
     // Bundles are handed out from the END of the shard's slot list, i.e. the frame is walked bottom-up: the
@@ -232,7 +219,7 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
                                      const float4* d_tables, const float* times, const float* blend, int passes,
                                      float4* d_accum, uint32_t* d_argb, int argb_packed, RmCounters* d_counters,
                                      unsigned long long* d_queue, int num_sms,
-                                     int block_threads, int round_bundles, int smem_map, int bottom_up, int half_groups, cudaStream_t stream) {
+                                     int block_threads, int round_bundles, int smem_map, int bottom_up, cudaStream_t stream) {
   if (shard.slots <= 0 || passes <= 0) return cudaSuccess;
   if (passes > RM_MAX_FUSED_PASSES) return cudaErrorInvalidValue;
   PersistParams P;
@@ -259,10 +246,8 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   const int warps_per_block = threads / 32;
   long long blocks = (P.bundles + warps_per_block - 1) / warps_per_block;
   if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;
-  const int K = round_bundles < 0 ? 0 : (round_bundles > 64 ? 64 : round_bundles);
-  P.round_bundles = K;
+  P.round_bundles = round_bundles != 0;
   P.bottom_up = bottom_up != 0;
-  P.half_groups = half_groups != 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;

@@ -129,7 +129,7 @@ def test_default_kernel_equals_round1_kernel_bit_for_bit(gpu_renderer):
     ref, argb_ref, _ = render_gpu(gpu_renderer, vol, opts, mcs, 200, 120, count=False)
     gpu_renderer.set_option(2, 0)
     try:
-        for block, group, smem in ((1024, 0, 1), (1024, 0, 0), (256, 0, 1), (1024, 1, 1), (256, 1, 0), (256, 4, 0), (0, -1, 1)):
+        for block, group, smem in ((1024, 0, 1), (1024, 0, 0), (256, 0, 1), (1024, 1, 1), (256, 1, 0), (256, 0, 0), (0, -1, 1)):
             gpu_renderer.set_option(10, block)
             gpu_renderer.set_option(11, group)
             gpu_renderer.set_option(12, smem)
