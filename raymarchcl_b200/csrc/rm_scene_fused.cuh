@@ -356,7 +356,10 @@ RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 de
 }
 
 // per-direction constants of the march: delta (renderer.cl:215) and 1 / (largest step in voxels)
-RM_DEV float3 march_delta(float3 dir, int steps, float& invS) {
+#ifndef RM_FUSED_MD_ATTR
+#define RM_FUSED_MD_ATTR RM_DEV
+#endif
+RM_FUSED_MD_ATTR float3 march_delta(float3 dir, int steps, float& invS) {
   const RmOpts& o = g_opts;
   const float3 delta = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
   const float sm = fmaxf(fmaxf(fabsf(delta.x) * (float)o.rx, fabsf(delta.y) * (float)o.ry), fabsf(delta.z) * (float)o.rz);
