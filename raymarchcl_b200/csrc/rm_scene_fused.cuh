@@ -483,21 +483,25 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
 
 RM_DEV float3 sky(float3 d) { return lerp3(g_opts.sky1, g_opts.sky2, d.y * 0.5f + 0.5f); }  // :259-261
 
-// renderer.cl:263-269
-RM_SHARED_FN float3 light_pos(Lane s, float px, float py, int i) {
+// renderer.cl:263-269. The jitter of the light positions, table[(uint)(px*1957 + py*2173 + time*4763.742)] *
+// lightScatter, is the same for every light and every surface of a pixel-sample: it is fetched and scaled once
+// (render_pixel_sample) and handed down instead of (px, py); lightPos(i) is then one vector add -- the same
+// operands and roundings as the reference's expression.
+RM_DEV float3 light_jitter(Lane s, float px, float py) {
   const uint32_t seed = f2u_wrap(px * 1957.0f + py * 2173.0f + s.time * 4763.742f);
-  return table_xyz(s, seed) * g_opts.lightScatter + g_opts.lightPos[i];
+  return table_xyz(s, seed) * g_opts.lightScatter;
 }
+RM_DEV float3 light_pos(float3 ljit, int i) { return ljit + g_opts.lightPos[i]; }
 
 RM_DEV float3 reflect3(float3 v, float3 n) { return v - n * (2.0f * dot3(v, n)); }  // :271-273
 
 // renderer.cl:275-290
-RM_SHARED_FN float3 atmosphere(Lane s, float px, float py, float3 ro, float3 rd, float distance, float3 col) {
+RM_SHARED_FN float3 atmosphere(float3 ljit, float3 ro, float3 rd, float distance, float3 col) {
   const RmOpts& o = g_opts;
   const float fa = 1.0f - expf(distance * distance * -o.fogPow);
   col = (sky(rd) - col) * fa + col;
   for (int i = 0; i < o.numLights; ++i) {
-    float3 lp = light_pos(s, px, py, i);
+    float3 lp = light_pos(ljit, i);
     const float d = cl_clamp(dot3(lp - ro, rd), 0.0f, distance);
     lp = rd * d + (ro - lp);
     col = o.lightColor[i] * (o.flareAmp / dot3(lp, lp)) + col;
@@ -568,7 +572,7 @@ RM_DEV float ambient_occlusion(RM_CNT c, Lane s, float3 pos, float3 n0) {
 #define RM_FUSED_OL_ATTR __device__ __noinline__
 #endif
 template <bool kCount, int kMap>
-RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float px, float py, float3 rd, float3 ipos, int mat, float3 n,
+RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float3 ljit, float3 rd, float3 ipos, int mat, float3 n,
                                         float3 reflectCol) {
   const RmOpts& o = g_opts;
   const RmMaterial& m = o.mat[mat];
@@ -577,7 +581,7 @@ RM_FUSED_OL_ATTR float3 object_lighting(RM_CNT c, Lane s, float px, float py, fl
   float3 spec = reflectCol * ao;
   float3 fin = f3s(0.0f);
   for (int i = 0; i < o.numLights; ++i) {
-    const float3 dl = light_pos(s, px, py, i) - ipos;
+    const float3 dl = light_pos(ljit, i) - ipos;
     const float ld2 = dot3(dl, dl);
     const float att = 1.0f / ld2;
     if (att > o.minLightAtt) {
@@ -608,7 +612,7 @@ RM_DEV int mat_index(int id) { return id < 0 ? 0 : (id > 3 ? 3 : id); }
 
 // renderer.cl:407-446 with basicSceneColor (:383-405) in its bounce loop
 template <bool kCount, int kMap>
-RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal, float3 ro, float3 rd) {
+RM_DEV float3 scene_color(RM_CNT c, Lane s, float3 ljit, float3 mcNormal, float3 ro, float3 rd) {
   const RmOpts& o = g_opts;
   RM_STAT_LEVEL(0);
   RM_STAT_SITE(0);
@@ -631,9 +635,9 @@ RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal,
         const Isec ri = sphere_trace<kCount, kMap>(c, bo, bd, o.maxDist, o.maxIter, false, true, false);  // (a reflection about an un-normalised normal is not a unit vector)
         float3 bc;
         if (ri.objectID < 0) bc = sky(bd);
-        else bc = object_lighting<kCount, kMap>(c, s, px, py, bd, ri.pos, mat_index(ri.objectID), ri.normal,
+        else bc = object_lighting<kCount, kMap>(c, s, ljit, bd, ri.pos, mat_index(ri.objectID), ri.normal,
                                                 sky(reflect3(bd, ri.normal)));
-        reflectCol = reflectCol + atmosphere(s, px, py, bo, bd, ri.distance, bc);
+        reflectCol = reflectCol + atmosphere(ljit, bo, bd, ri.distance, bc);
         if (ri.objectID < 0) break;
         if (o.mat[mat_index(ri.objectID)].r0 < 0.001f) break;
         bpos = ri.pos;
@@ -643,9 +647,9 @@ RM_DEV float3 scene_color(RM_CNT c, Lane s, float px, float py, float3 mcNormal,
       reflectCol = sky(reflect3(rd, n));
     }
     RM_STAT_LEVEL(0);
-    col = object_lighting<kCount, kMap>(c, s, px, py, rd, isec.pos, mi, n, reflectCol);
+    col = object_lighting<kCount, kMap>(c, s, ljit, rd, isec.pos, mi, n, reflectCol);
   }
-  return atmosphere(s, px, py, ro, rd, isec.distance, col);
+  return atmosphere(ljit, ro, rd, isec.distance, col);
 }
 
 // One work-item of RenderImage (renderer.cl:478-494; initRenderState :467-476, cameraRayLookat
@@ -664,7 +668,7 @@ RM_DEV float3 render_pixel_sample(RM_CNT c, Lane s, int id) {
   float vy = py / (float)o.height * o.fov - o.fov * 0.5f;
   vy = vy * -o.invAspect;
   const float3 rd = unit3(right * vx + cross3(right, fwd) * vy + fwd);
-  return scene_color<kCount, kMap>(c, s, px, py, mcNormal, eye, rd) * o.exposure;
+  return scene_color<kCount, kMap>(c, s, light_jitter(s, px, py), mcNormal, eye, rd) * o.exposure;
 }
 
 }  // namespace fused
