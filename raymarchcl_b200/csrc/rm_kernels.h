@@ -73,7 +73,7 @@ cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, i
 // (rm_scene_fused.cuh, rm_render_persist.cu), RM_OPT_KERNEL = 0 ----
 #define RM_PERSIST_MAX_SMEM (200 * 1024) // largest 4-bit distance map staged into shared memory
 #define RM_PERSIST_DEFAULT_BLOCK 256      // measured best layout on B200 (C2): 256 threads x 5 blocks per SM ...
-#define RM_PERSIST_DEFAULT_ROUND 1        // ... drawing bundles in block-synchronous rounds
+#define RM_PERSIST_DEFAULT_ROUND 0        // ... drawing bundles in block-synchronous rounds
 // How many of `available` consecutive fusable passes one launch should take: all (<= 32) when they
 // fill >= 80 % of a warp's lanes as whole pixels x passes groups, else the largest power of two.
 inline int rm_persist_pick_passes(int available) {

@@ -39,6 +39,33 @@ RM_UNIT3_ATTR float3 unit3(float3 a) {
   const float l = len3(a);
   return l == 0.0f ? a : a / l;
 }
+// 1 / x for a NORMAL x (every caller checks |x| >= 1e-5 first): the bare MUFU.RCP. __fdividef(1, x) is the same
+// instruction wrapped in six more that pre-scale a denormal divisor (this build keeps denormals). Only used for
+// conservative bounds (march windows, skip lengths), never for a value of the result.
+RM_DEV float rcp_fast(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+// (x, y) += (dx, dy) as ONE instruction. Blackwell (sm_100) has packed fp32 arithmetic -- SASS FADD2 / FMUL2 / FFMA2,
+// PTX add / mul / fma .f32x2 on 64-bit register pairs -- that performs two IEEE round-to-nearest operations per issued
+// instruction: the same bits as two scalar adds (no flush to zero), in half the issue slots. The operands stay
+// ordinary floats in the source (ptxas allocates x, y and dx, dy to aligned pairs and the packing moves vanish), so
+// that a conditional scalar add on one of them next to it costs nothing extra. The host build (tests/hostsim) uses
+// two scalar adds.
+RM_DEV void add2(float& x, float& y, float dx, float dy) {
+#ifdef __CUDA_ARCH__
+  asm("{\n .reg .b64 a, b;\n mov.b64 a, {%0, %1};\n mov.b64 b, {%2, %3};\n add.rn.f32x2 a, a, b;\n mov.b64 {%0, %1}, a;\n}"
+      : "+f"(x), "+f"(y) : "f"(dx), "f"(dy));
+#else
+  x += dx;
+  y += dy;
+#endif
+}
 RM_DEV float3 lerp3(float3 a, float3 b, float t) { return a + (b - a) * t; }
 // (uint)float with two's-complement wrap of the truncated value, also for negatives (8c-1)
 RM_DEV uint32_t f2u_wrap(float f) { return (uint32_t)(long long)f; }

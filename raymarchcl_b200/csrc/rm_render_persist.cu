@@ -70,6 +70,11 @@ __device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
 // block). Every block stages its own copy of the map, so the 128 KiB map of a 256^3 volume only fits
 // the first layout. (Measured and dropped, C2 ms per frame against 36.7 for 256 x 5: 640 x 2 at 48 registers
 // 41.2 before the march rewrite, like 1024 x 1; 128 x 10: +15 %; 192 x 6 and 384 x 3 at 56 registers: 38.1 / 38.3.)
+// (the small layout as macros so that an experiment can rebuild with another one: build.py -DRM_PERSIST_SMALL_T=128 ...)
+#ifndef RM_PERSIST_SMALL_T
+#define RM_PERSIST_SMALL_T 256
+#define RM_PERSIST_SMALL_B 5
+#endif
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ PersistParams P) {
@@ -159,6 +164,7 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
       const float4 old = P.accum[id];
       p = f3(old.x, old.y, old.z);
     }
+#pragma unroll 1  // (once per bundle: not worth four copies of the body)
     for (int k = 0; k < m; ++k) {
       const float3 ck = f3(__shfl_sync(0xffffffffu, c.x, base + k), __shfl_sync(0xffffffffu, c.y, base + k),
                            __shfl_sync(0xffffffffu, c.z, base + k));
@@ -209,7 +215,7 @@ cudaError_t launch_any(bool count, int threads, const RmShard& shard, const Pers
                        cudaStream_t stream) {
   // (the counting kernels visit every sample anyway: only the map's location matters to them)
   if (count) return launch<true, kMap & fused::kMapNib, 1024, 1>(shard, P, blocks, smem, dev, stream);
-  if (threads == 256) return launch<false, kMap, 256, 5>(shard, P, blocks, smem, dev, stream);
+  if (threads == RM_PERSIST_SMALL_T) return launch<false, kMap, RM_PERSIST_SMALL_T, RM_PERSIST_SMALL_B>(shard, P, blocks, smem, dev, stream);
   return launch<false, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
 }
 
@@ -239,8 +245,8 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
   P.nib = accel.nib;
   P.nib_bytes = accel.nib_bytes;
-  const int threads = d_counters ? 1024 : (block_threads == 256 ? 256 : 1024);
-  const int blocks_per_sm = threads == 1024 ? 1 : 5;
+  const int threads = d_counters ? 1024 : (block_threads == 256 ? RM_PERSIST_SMALL_T : 1024);
+  const int blocks_per_sm = threads == 1024 ? 1 : RM_PERSIST_SMALL_B;
   const bool use_nib = smem_map != 0 && accel.nib != nullptr && accel.nib_bytes > 0 &&
                        accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
   const int warps_per_block = threads / 32;

@@ -269,9 +269,9 @@ RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
   }
   bool found = false;
   const unsigned nib = (kMap & kMapNib) ? nib_base() : 0u;
-  const float rxf = kPow2 ? 1.0f : g_accel.rxf, ryf = kPow2 ? 1.0f : g_accel.ryf, rzf = kPow2 ? 1.0f : g_accel.rzf;
   const unsigned rx = g_opts.rx, ry = g_opts.ry, rz = g_opts.rz;
   const int cs = (kMap & kMapCell4) ? 2 : g_accel.cell_shift, my = g_accel.my, mx = g_accel.mx;
+  const float rxf = kPow2 ? 1.0f : g_accel.rxf, ryf = kPow2 ? 1.0f : g_accel.ryf, rzf = kPow2 ? 1.0f : g_accel.rzf;
   while (rem > 0) {
     const int x = kPow2 ? f2i_sat(px) : f2i_sat(px * rxf);
     const int y = kPow2 ? f2i_sat(py) : f2i_sat(py * ryf);
@@ -295,9 +295,9 @@ RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
     rem -= n;
     RM_STAT_SKIP(n);
 #pragma unroll 1
-    for (int h = n >> 1; h > 0; --h) {
-      px += delta.x; py += delta.y; pz += delta.z;
-      px += delta.x; py += delta.y; pz += delta.z;
+    for (int h = n >> 1; h > 0; --h) {  // (x, y) as one FADD2 (rm_math.cuh:add2): 7 instructions per two samples
+      add2(px, py, delta.x, delta.y); pz += delta.z;
+      add2(px, py, delta.x, delta.y); pz += delta.z;
     }
     if (n & 1) { px += delta.x; py += delta.y; pz += delta.z; }
   }
@@ -359,12 +359,14 @@ RM_FUSED_SD_ATTR Hit scene_distance(RM_CNT c, float3 rpos, float3 dir, float3 de
 #ifndef RM_FUSED_MD_ATTR
 #define RM_FUSED_MD_ATTR RM_DEV
 #endif
-RM_FUSED_MD_ATTR float3 march_delta(float3 dir, int steps, float& invS) {
+struct Delta { float3 d; float invS; };
+RM_FUSED_MD_ATTR Delta march_delta(float3 dir, int steps) {
   const RmOpts& o = g_opts;
-  const float3 delta = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
-  const float sm = fmaxf(fmaxf(fabsf(delta.x) * (float)o.rx, fabsf(delta.y) * (float)o.ry), fabsf(delta.z) * (float)o.rz);
-  invS = sm > 5e-4f ? __fdividef(1.0f, sm) : 2000.0f;
-  return delta;
+  Delta r;
+  r.d = (dir / ((float)steps * 0.5f)) * o.invVoxelScale;
+  const float sm = fmaxf(fmaxf(fabsf(r.d.x) * (float)o.rx, fabsf(r.d.y) * (float)o.ry), fabsf(r.d.z) * (float)o.rz);
+  r.invS = sm > 5e-4f ? rcp_fast(sm) : 2000.0f;
+  return r;
 }
 
 // The march window of a trace (see rm_scene_plain.cuh:march_window for the argument).
@@ -387,7 +389,7 @@ RM_DEV void march_window(float3 ro, float3 rd, float maxDist, float& tin, float&
     if (fabsf(rd_[i]) < kTiny) {
       if (l > 0.0f || h < 0.0f) miss = true;
     } else {
-      const float inv = __fdividef(1.0f, rd_[i]);
+      const float inv = rcp_fast(rd_[i]);
       const float t0 = l * inv, t1 = h * inv;
       a = fmaxf(a, fminf(t0, t1));
       b = fminf(b, fmaxf(t0, t1));
@@ -408,8 +410,9 @@ RM_FUSED_ST_ATTR Isec sphere_trace(RM_CNT c, float3 ro, float3 rd, float maxDist
   const RmOpts& o = g_opts;
   RM_STAT_TRACE();
   RM_STAT_EVENT(wantSurface ? 6 : 7);
-  float invS;
-  const float3 delta = march_delta(rd, o.maxVoxelIter, invS);
+  const Delta md = march_delta(rd, o.maxVoxelIter);
+  const float3 delta = md.d;
+  const float invS = md.invS;
   Hit j;
   j.dist = 0.0f; j.flags = 0; j.p = f3s(0.0f);
   float jg = 0.0f;  // ground distance of the last evaluation (the ground's "id" is (int)g, renderer.cl:211)
@@ -500,6 +503,7 @@ RM_SHARED_FN float3 atmosphere(float3 ljit, float3 ro, float3 rd, float distance
   const RmOpts& o = g_opts;
   const float fa = 1.0f - expf(distance * distance * -o.fogPow);
   col = (sky(rd) - col) * fa + col;
+#pragma unroll 1  // (ptxas unrolls this four times otherwise: 1.6 KB of code for a loop that runs 1-4 times per surface)
   for (int i = 0; i < o.numLights; ++i) {
     float3 lp = light_pos(ljit, i);
     const float d = cl_clamp(dot3(lp - ro, rd), 0.0f, distance);
@@ -548,9 +552,10 @@ RM_DEV float ambient_occlusion(RM_CNT c, Lane s, float3 pos, float3 n0) {
       RM_STAT_EVENT(18);
       hdist = g < 1e5f ? g : 1e5f;
     } else {
-      float invS;
       const int msteps = o.maxVoxelIter / 2;
-      const float3 delta = march_delta(n, msteps, invS);
+      const Delta md = march_delta(n, msteps);
+      const float3 delta = md.d;
+      const float invS = md.invS;
       int limit = msteps;
       if (!kCount && o.aoAmp >= 0.0f && d > 0.0f) {
         // (n is a unit vector -- or 0, and then the march does not move and its length is immaterial --, so the
