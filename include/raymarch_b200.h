@@ -85,15 +85,16 @@ typedef enum rm_option {
   RM_OPT_WAVE_CHUNK = 8,   /* kernel 3: (pixel, pass) items per chunk of the pipeline (1024..2^24, default 2^24) */
   RM_OPT_WAVE_REFILL = 9,  /* kernel 3: the trace kernel hands new rays to idle lanes once this many lanes of a
                               warp are idle (1 = at once ... 32 = the warp starts 32 rays together) */
-  RM_OPT_PERSIST_BLOCK = 10, /* kernel 0: resident block layout: 0 = default, 1024 (x 1 block per SM, 64 registers)
-                               or 256 (x 5, 48 registers) threads */
-  RM_OPT_PERSIST_SMEM = 12,  /* kernel 0: 1 = stage the 4-bit distance map into shared memory by bulk TMA (cp.async.bulk +
-                               mbarrier) when a copy per resident block fits the SM -- 128 KiB at 256^3, so with the
-                               1024-thread layout only; 0 (default) = read the byte map from global memory / L1, which
-                               measured faster at every volume size */
+  RM_OPT_PERSIST_BLOCK = 10, /* kernel 0: resident block layout: 1024 (x 1 block per SM, 64 registers) or 256 (x 5, 48 registers)
+                               threads; 0 (default) = per launch: 1024 when the distance map is staged into shared memory
+                               (next option) and the launch is long enough to pay for it, else 256 */
+  RM_OPT_PERSIST_SMEM = 12,  /* kernel 0: stage the 4-bit distance map into shared memory by bulk TMA (cp.async.bulk + mbarrier)
+                               when a copy per resident block fits the SM (128 KiB at 256^3: 1024-thread layout only):
+                               0 = never (byte map from global memory / L1), 1 = whenever it fits the layout in use,
+                               2 (default) = with the 1024-thread layout (measured: DESIGN.md 4) */
   RM_OPT_PERSIST_ORDER = 13, /* kernel 0: 1 (default) = walk the frame bottom-up so that the launch ends on the (cheap) top rows; 0 = top-down */
   RM_OPT_PERSIST_GROUP = 11  /* kernel 0: 0 = every warp draws its next work bundle on its own; 1 = the warps of a block draw
-                               one bundle each together and meet at the block barrier per draw; -1 = default (1) */
+                               one bundle each together and meet at the block barrier per draw; -1 = default (0) */
 } rm_option;
 
 /* ---- lifetime (replaces cl/select-platform .. cl/init-state, core.clj:121-128; cl/release :213) ---- */

@@ -77,8 +77,7 @@ struct rm_ctx {
   unsigned long long* d_queue = nullptr;  // [0] work queue head of the warp kernel, [1] bundle tickets of the default kernel
   int persist_block = 0;                  // threads of the default kernel's block; 0 = library default
   int persist_bottom_up = 1;              // RM_OPT_PERSIST_ORDER
-  int persist_smem = 0;                   // 1: stage the 4-bit distance map into shared memory by bulk TMA when it fits (RM_OPT_PERSIST_SMEM);
-                                          // measured slower than the L1-resident byte map at every volume size, hence off
+  int persist_smem = RM_PERSIST_DEFAULT_SMEM;  // stage the 4-bit distance map into shared memory by bulk TMA: 0 never, 1 when it fits, 2 auto (RM_OPT_PERSIST_SMEM);
   int persist_group = -1;                 // 1 = block-synchronous rounds of the default kernel; 0 = free-running warps; -1 = default
   unsigned* d_watchdog = nullptr;         // 16 words, see rm_launch_render_warp
   unsigned trip_limit = 1u << 28;
@@ -385,7 +384,7 @@ int launch_passes(rm_ctx* c, const RmOpts* passes, int n, const float4* d_tables
         } else if (c->kernel_kind == 0) {
           int packed = 0;
           uint32_t* argb = fused_argb_target(c, &packed);
-          // defaults (measured on B200, C2): 256 x 5 blocks with block-synchronous rounds
+          // defaults (measured on B200): layout and map location picked per launch, free-running warps
           const int persist_block = c->persist_block ? c->persist_block : RM_PERSIST_DEFAULT_BLOCK;
           const int persist_group = c->persist_group >= 0 ? c->persist_group : RM_PERSIST_DEFAULT_ROUND;
           e = rm_launch_render_persist(passes[i], c->shard, c->accel.view, d_tables + i * tstride, times, blend, m, c->d_accum,
@@ -1156,7 +1155,9 @@ int rm_set_option(rm_ctx* c, int option, int64_t value) {
       c->persist_bottom_up = value != 0;
       return RM_OK;
     case RM_OPT_PERSIST_SMEM:
-      c->persist_smem = value != 0;
+      if (value < 0 || value > 2)
+        return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_SMEM: 0 (never), 1 (whenever the map fits the layout) or 2 (default: with the 1024-thread layout)");
+      c->persist_smem = (int)value;
       return RM_OK;
     case RM_OPT_PERSIST_GROUP:
       if (value < -1 || value > 1) return fail(c, RM_ERR_INVALID_ARG, "RM_OPT_PERSIST_GROUP: -1 (default), 0 (free-running warps) or 1 (block-synchronous rounds)");

@@ -72,8 +72,10 @@ cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, i
 // ---- default kernel: persistent warps, distance map in shared memory, blend + tonemap folded in
 // (rm_scene_fused.cuh, rm_render_persist.cu), RM_OPT_KERNEL = 0 ----
 #define RM_PERSIST_MAX_SMEM (200 * 1024) // largest 4-bit distance map staged into shared memory
-#define RM_PERSIST_DEFAULT_BLOCK 256      // measured best layout on B200 (C2): 256 threads x 5 blocks per SM ...
-#define RM_PERSIST_DEFAULT_ROUND 0        // ... drawing bundles in block-synchronous rounds
+#define RM_PERSIST_DEFAULT_BLOCK 0        // 0 = chosen per launch (rm_launch_render_persist): 1024 x 1 + TMA-staged map for long launches, else 256 x 5
+#define RM_PERSIST_DEFAULT_SMEM 2         // 0 never, 1 whenever the map fits the layout, 2 = with the 1024-thread layout only
+#define RM_PERSIST_DEFAULT_ROUND 0        // free-running warps (1 = block-synchronous rounds: faster while the code was 58 KB, slower at 47 KB)
+#define RM_PERSIST_AUTO_BUNDLES_PER_WARP 16  // "long launch": at least this many bundles per resident warp slot of the 1024 x 1 layout
 // How many of `available` consecutive fusable passes one launch should take: all (<= 32) when they
 // fill >= 80 % of a warp's lanes as whole pixels x passes groups, else the largest power of two.
 inline int rm_persist_pick_passes(int available) {

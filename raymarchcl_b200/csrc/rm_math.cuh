@@ -9,10 +9,29 @@
 
 RM_DEV float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
 RM_DEV float3 f3s(float s) { return make_float3(s, s, s); }
+#if defined(__CUDA_ARCH__) && defined(RM_PACKED_F3)
+// float3 arithmetic with the x and y lanes as one packed instruction (FADD2 / FMUL2, see add2 below)
+#define RM_F3_PACKED_OP(name, ptx)                                                                            \
+  RM_DEV float3 name(float3 a, float3 b) {                                                                    \
+    float3 r;                                                                                                 \
+    asm("{\n .reg .b64 a, b;\n mov.b64 a, {%2, %3};\n mov.b64 b, {%4, %5};\n " ptx ".rn.f32x2 a, a, b;\n mov.b64 {%0, %1}, a;\n}" \
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                     \
+    return r;                                                                                                 \
+  }
+RM_F3_PACKED_OP(f3_add_xy, "add")
+RM_F3_PACKED_OP(f3_sub_xy, "sub")
+RM_DEV float3 operator+(float3 a, float3 b) { float3 r = f3_add_xy(a, b); r.z = a.z + b.z; return r; }
+RM_DEV float3 operator-(float3 a, float3 b) { float3 r = f3_sub_xy(a, b); r.z = a.z - b.z; return r; }
+// (multiplies stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad false and explicit
+//  rounding modifiers -- one rounding instead of the reference's two)
+RM_DEV float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RM_DEV float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+#else
 RM_DEV float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 RM_DEV float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 RM_DEV float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 RM_DEV float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+#endif
 RM_DEV float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
 RM_DEV float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
 RM_DEV float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }

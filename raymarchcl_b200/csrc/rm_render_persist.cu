@@ -27,6 +27,9 @@
 // Compiled with -fmad=false like the rest of the library (pinned two-rounding evaluation order).
 #include <mutex>
 
+// float3 adds / subtracts of this kernel as packed FADD2 on the (x, y) lanes (rm_math.cuh; Blackwell-only SASS). The
+// other render kernels keep scalar arithmetic, so tests that compare kernels bit for bit compare the two forms as well.
+#define RM_PACKED_F3 1
 #include "rm_kernels.h"
 #include "rm_scene_fused.cuh"
 
@@ -245,10 +248,20 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
   P.nib = accel.nib;
   P.nib_bytes = accel.nib_bytes;
-  const int threads = d_counters ? 1024 : (block_threads == 256 ? RM_PERSIST_SMALL_T : 1024);
+  // Layout and map location (RM_OPT_PERSIST_BLOCK / _SMEM; 0 / 2 = pick here). One 1024-thread block per SM with the
+  // 4-bit distance map staged into its shared memory by TMA is the fastest form once a launch is long enough to pay
+  // for 148 blocks each pulling the map in (B200, C2: 30.99 ms against 31.43 for 256 x 5 with the byte map in L1 / L2;
+  // C1's 2048 bundles: 0.403 against 0.386); five 256-thread blocks per SM with the map in shared memory are not
+  // (128^3: 30.18 against 30.03), so the automatic choice couples the two.
+  const bool fits_big = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= (unsigned)RM_PERSIST_MAX_SMEM;
+  const bool long_launch = P.bundles >= (long long)RM_PERSIST_AUTO_BUNDLES_PER_WARP * num_sms * 32;
+  int threads;
+  if (d_counters) threads = 1024;
+  else if (block_threads == 0) threads = (smem_map != 0 && fits_big && long_launch) ? 1024 : RM_PERSIST_SMALL_T;
+  else threads = block_threads == 256 ? RM_PERSIST_SMALL_T : 1024;
   const int blocks_per_sm = threads == 1024 ? 1 : RM_PERSIST_SMALL_B;
-  const bool use_nib = smem_map != 0 && accel.nib != nullptr && accel.nib_bytes > 0 &&
-                       accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
+  const bool fits = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
+  const bool use_nib = fits && (smem_map == 1 || (smem_map == 2 && threads == 1024));
   const int warps_per_block = threads / 32;
   long long blocks = (P.bundles + warps_per_block - 1) / warps_per_block;
   if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;

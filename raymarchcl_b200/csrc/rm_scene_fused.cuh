@@ -289,7 +289,7 @@ RM_DEV bool march_fast(float3& p, float3 delta, int rem, float invS) {
     }
     // samples consumed by this iteration: this one plus the ones known to be empty
     const float dm1 = __int_as_float(0x4b000000 + d) - 8388609.0f;
-    const int k = __float_as_int((dm1 * A - B) + 12582912.0f) - 0x4b400000;
+    const int k = __float_as_int(fmaf(dm1, A, -B) + 12582912.0f) - 0x4b400000;  // (own bound, not reference arithmetic: one rounding is fine)
     const int n = 1 + (k > 0 ? k : 0);
     if (n >= rem) break;  // the march runs out inside space known to be empty: a miss
     rem -= n;

@@ -129,7 +129,8 @@ def test_default_kernel_equals_round1_kernel_bit_for_bit(gpu_renderer):
     ref, argb_ref, _ = render_gpu(gpu_renderer, vol, opts, mcs, 200, 120, count=False)
     gpu_renderer.set_option(2, 0)
     try:
-        for block, group, smem in ((1024, 0, 1), (1024, 0, 0), (256, 0, 1), (1024, 1, 1), (256, 1, 0), (256, 0, 0), (0, -1, 1)):
+        for block, group, smem in ((1024, 0, 1), (1024, 0, 0), (256, 0, 1), (1024, 1, 1), (256, 1, 0), (256, 0, 0), (0, -1, 1),
+                                   (0, -1, 2), (1024, -1, 2), (256, -1, 2), (0, -1, 0)):
             gpu_renderer.set_option(10, block)
             gpu_renderer.set_option(11, group)
             gpu_renderer.set_option(12, smem)
@@ -139,7 +140,7 @@ def test_default_kernel_equals_round1_kernel_bit_for_bit(gpu_renderer):
     finally:
         gpu_renderer.set_option(10, 0)
         gpu_renderer.set_option(11, -1)
-        gpu_renderer.set_option(12, 0)
+        gpu_renderer.set_option(12, 2)
 
 
 def test_map_too_large_for_shared_memory_uses_the_global_map(gpu_renderer, oracle):
@@ -161,7 +162,7 @@ def test_map_too_large_for_shared_memory_uses_the_global_map(gpu_renderer, oracl
         b, argb_b, _ = render_gpu(gpu_renderer, vol, opts, mcs, w, h, count=False)
     finally:
         gpu_renderer.set_option(3, 0)
-        gpu_renderer.set_option(12, 0)
+        gpu_renderer.set_option(12, 2)
     assert np.array_equal(cnt, ref_cnt)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     check_frame(b, ref_px, argb_b, oracle.tonemap(ref_px, opts[0]))
@@ -198,7 +199,7 @@ def test_distance_map_staged_by_tma_matches_oracle(gpu_renderer, oracle, kw, blo
         a, argb_a, cnt = render_gpu(r, vol, opts, mcs, w, h, count=True)
         b, argb_b, _ = render_gpu(r, vol, opts, mcs, w, h, count=False)
     finally:
-        r.set_option(12, 0)
+        r.set_option(12, 2)
         r.set_option(10, 0)
     assert np.array_equal(cnt, ref_cnt)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(b.view(np.uint32), base.view(np.uint32))

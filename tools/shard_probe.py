@@ -33,13 +33,13 @@ with Renderer(0) as r:
         return r.stats()["render_ms"] / args.steps
 
     for knob in args.knobs.split(","):
-        b, k, up = [int(x) for x in knob.split(":")]
-        r.set_option(10, b); r.set_option(11, k); r.set_option(13, up)
+        b, k, up, sm = ([int(x) for x in knob.split(":")] + [2])[:4]  # block : rounds : bottom-up [: shared-memory map 0/1/2]
+        r.set_option(10, b); r.set_option(11, k); r.set_option(13, up); r.set_option(12, sm)
         full = timed(0, 1, 32, 32)
         for tile in args.tiles.split(","):
             tw, th = [int(x) for x in tile.split("x")]
             ts = [timed(rank, args.world, tw, th) for rank in range(args.world)]
-            print(json.dumps({"block": b, "round": k, "bottom_up": up, "tile": tile, "world": args.world, "full_ms": round(full, 3),
+            print(json.dumps({"block": b, "round": k, "bottom_up": up, "smem": sm, "tile": tile, "world": args.world, "full_ms": round(full, 3),
                               "ideal_ms": round(full / args.world, 3), "shard_ms_min": round(min(ts), 3),
                               "shard_ms_mean": round(sum(ts) / len(ts), 3), "shard_ms_max": round(max(ts), 3),
                               "efficiency_max": round(full / args.world / max(ts), 4)}), flush=True)
