@@ -1,12 +1,15 @@
 // rm_render_persist.cu -- the DEFAULT RenderImage kernel (renderer.cl:478-494) for sm_100a, with
 // the frame's blend (renderer.cl:492) and TonemapImage (renderer.cl:496-508) folded into it.
 //
-//   persistent   148 x 5 blocks of 256 threads (48 registers, 40 warps per SM) live for the whole launch
-//                and draw work bundles from a global ticket counter -- in block-synchronous rounds: the
-//                8 warps of a block take 8 consecutive bundles and meet at the block barrier before the
-//                next draw. Warps that draw on their own (measured: 38.2 vs 36.7 ms per C2 frame) drift
-//                through the routine independently and stream its 68 KB of code through the 32 KB
-//                instruction cache again and again; the warps of a synchronised block share the lines.
+//   persistent   the blocks live for the whole launch and every WARP draws its next work bundle from a global
+//                ticket counter as soon as it is done with the last one. Two layouts, picked per launch
+//                (rm_launch_render_persist): one 1024-thread block per SM (64 registers, 32 warps) with the
+//                distance map in shared memory (TMA, below) for launches long enough to pay for staging it, and
+//                five 256-thread blocks per SM (48 registers, 40 warps) with the byte map in global memory for
+//                short ones. (An option, RM_OPT_PERSIST_GROUP, makes the warps of a block draw together and meet
+//                at the block barrier per draw: the warps then share the instruction lines they pull in. That
+//                was 4 % faster while the kernel's code was 58-68 KB against a 32 KB instruction cache and is
+//                3 % slower now that it is 47 KB: profiles/r02_scheduling_ab.md.)
 //   bundles      a bundle is 32 / m neighbouring pixels x the m passes of the launch, pass-minor:
 //                the lanes of a warp render the SAME pixels in different passes (rays that differ
 //                only by jitter), which is what keeps their control flow together.
@@ -18,11 +21,13 @@
 //                (gamma of the launch's opts) -- into the context's frame, a caller's gather buffer or,
 //                in a multi-GPU group, straight into GPU 0's frame over NVLink peer memory;
 //                rm_tonemap returns that buffer when nothing changed.
-//   TMA          opt-in (RM_OPT_PERSIST_SMEM): on block start one thread arms an mbarrier and issues
-//                cp.async.bulk copies of the 4-bit macro-cell distance map (128 KiB at 64^3 cells) into
-//                shared memory; the march reads it with LDS (rm_scene_fused.cuh). It removes the map's
-//                long-scoreboard stalls and a third of the L2 traffic and is slower at every volume
-//                size (one 1024-thread block per SM at 256^3; nibble extraction elsewhere): DESIGN.md 4.
+//   TMA          on block start one thread arms an mbarrier and issues cp.async.bulk copies of the 4-bit macro-cell
+//                distance map (128 KiB at 64^3 cells) into shared memory; every thread waits on the barrier and the
+//                march then reads the map with LDS (rm_scene_fused.cuh): no long-scoreboard stall on the march's
+//                first load, a third less L2 traffic. One copy per resident block, so at 256^3 it needs the
+//                1024-thread layout. B200, C2: 30.8 ms against 31.4 for 256 x 5 with the byte map in L1 / L2.
+//   FADD2        float3 adds and the march recurrence use Blackwell's packed fp32 add on the (x, y) lanes
+//                (rm_math.cuh): the same IEEE results in two thirds of the issue slots.
 //
 // Compiled with -fmad=false like the rest of the library (pinned two-rounding evaluation order).
 #include <mutex>
@@ -71,8 +76,8 @@ __device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
 // Layouts (threads per block x resident blocks per SM), RM_OPT_PERSIST_BLOCK: 1024 x 1 (64 registers,
 // 32 warps per SM, room for a 200 KB distance map) and 256 x 5 (48 registers, 40 warps, <= 40 KB map per
 // block). Every block stages its own copy of the map, so the 128 KiB map of a 256^3 volume only fits
-// the first layout. (Measured and dropped, C2 ms per frame against 36.7 for 256 x 5: 640 x 2 at 48 registers
-// 41.2 before the march rewrite, like 1024 x 1; 128 x 10: +15 %; 192 x 6 and 384 x 3 at 56 registers: 38.1 / 38.3.)
+// the first layout. (Measured and dropped, C2 ms per frame, free-running warps, byte map: 256 x 5 33.19, 256 x 6
+// 33.03, 192 x 6 33.15, 512 x 2 33.76, 256 x 4 33.87, 128 x 8 35.50, 128 x 10 36.90.)
 // (the small layout as macros so that an experiment can rebuild with another one: build.py -DRM_PERSIST_SMALL_T=128 ...)
 #ifndef RM_PERSIST_SMALL_T
 #define RM_PERSIST_SMALL_T 256
@@ -120,14 +125,15 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
   s.time = P.times[lane_used ? pass : 0];
 
   // Scheduling granularity (round_bundles, RM_OPT_PERSIST_GROUP).
-  //   0: every warp draws its next bundle on its own -- no warp ever waits for another, but the warps of
-  //      an SM drift through the routine independently and the kernel's code (2x the 32 KB L1.5 instruction
-  //      cache, most of it touched once per bundle) is fetched again and again: ncu stall_no_instruction
-  //      3.5 per issue.
+  //   0 (default): every warp draws its next bundle on its own -- no warp ever waits for another, but the warps of
+  //      an SM drift through the routine independently and the kernel's code (larger than the 32 KB L1.5
+  //      instruction cache) is fetched again and again: ncu stall_no_instruction 2.0 per issue at 256 x 5, 1.0
+  //      at 1024 x 1.
   //   1: the block draws one bundle per warp together (warp w takes bundle t0 + w) and meets at its barrier
   //      before the next draw. Its warps then run the same phases of the routine at about the same time and
-  //      share the instruction lines they pull in (stall_no_instruction 0.9), at the price of waiting for the
-  //      slowest warp of a round (17 % of the warp-time) -- and still 4 % faster.
+  //      share the instruction lines they pull in (stall_no_instruction 0.6), at the price of waiting for the
+  //      slowest warp of a round (17 % of the warp-time). Which one wins is a matter of code size: rounds by 4 %
+  //      at 58 KB (36.7 vs 38.2 ms, 34.8 vs 35.4), free-running by 3 % at 47 KB (31.4 vs 32.3).
   //   (Measured and removed: 2 / 4 bundles per warp per round, two half-block sync groups over named barriers,
   //    named-barrier groups inside a 1024-thread block: all slower, profiles/r02_scheduling_ab.md.)
   __shared__ unsigned long long s_ticket[2];

@@ -160,3 +160,20 @@ def test_pass_chunking_of_the_default_kernel():
             left -= m
         assert sum(chunks) == n
     assert [lib.sim_pick_passes(k) for k in (16, 100, 11, 17, 3, 33)] == [16, 32, 8, 16, 3, 32]
+
+
+def test_packed_fp32_is_used_and_never_contracted():
+    """The default kernel adds the (x, y) lanes of its float3 values with Blackwell's packed FADD2 (csrc/rm_math.cuh).
+    ptxas contracts a packed multiply feeding a packed add into FFMA2 even with --fmad false and explicit .rn
+    modifiers -- one rounding where the reference has two -- so the library must hold packed ADDS only: no FFMA2 and no
+    FMUL2 anywhere in its SASS."""
+    import shutil
+    import subprocess
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libraymarch_b200.so not built")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert len(re.findall(r"\bFADD2\b", sass)) > 100
+    assert not re.findall(r"\b(FFMA2|FMUL2)\b", sass)

@@ -26,7 +26,7 @@ ncu_cap() {  # name, extra bench args
     > gpurun_out/${TAG}_ncu_${name}.log 2>&1
   echo "ncu $name rc=$?"
 }
-ncu_cap persist_c2                      # the default: 256 x 5, block-synchronous rounds, global map
-ncu_cap persist_c2_tma --opt 10=1024 --opt 11=0 --opt 12=1   # 1024 x 1, distance map in shared memory via bulk TMA
-ncu_cap persist_c2_free --opt 11=0      # 256 x 5, free-running warps
+ncu_cap final_c2                                              # the default: 1024 x 1, free-running warps, distance map staged into shared memory by TMA
+ncu_cap final_c2_256x5 --opt 10=256 --opt 12=0                # 256 x 5, free-running, byte map in global memory (the default of short launches)
+ncu_cap final_c2_rounds --opt 10=256 --opt 12=0 --opt 11=1    # ... with block-synchronous rounds
 ls -la gpurun_out | tail -30
