@@ -13,7 +13,9 @@
 //   * the march loop is rewritten for few paths and few instructions (march_fast below);
 //   * the distance map can be read from SHARED MEMORY (kMapNib): 4 bits per macro-cell (Chebyshev
 //     distance saturated at 15), staged once per resident block with a bulk TMA copy (cp.async.bulk +
-//     mbarrier, rm_render_persist.cu). Opt-in: measured slower than the L1-resident byte map.
+//     mbarrier, rm_render_persist.cu): the default of long launches, in the 1024-thread layout;
+//     the byte map in global memory / L1 otherwise;
+//   * float3 adds and the march recurrence use Blackwell's packed FADD2 on the (x, y) lanes (rm_math.cuh).
 //
 // tests/hostsim compiles this header for the host (RM_NIB_BASE is then a plain pointer) and compares
 // the routine with the oracle bit for bit.
