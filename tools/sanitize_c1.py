@@ -18,17 +18,23 @@ with Renderer(0) as r:
         ref = None
         for k in kernels:
             r.set_option(2, k)
-            for count in (True, False):
-                r.set_volume(vol)
-                r.clear_accum(kw["width"], kw["height"])
-                r.count_work(count)
-                r.render_frame(opts, mcs)
-                px = r.read_accum()
-                argb = r.tonemap(opts[0])
-                if ref is None:
-                    ref = px
-                assert np.array_equal(px.view(np.uint32), ref.view(np.uint32)), (k, count)
-            print(f"kernel {k}: {kw['width']}x{kw['height']}x{kw['iters']} ok", flush=True)
+            # kernel 0: (block layout, scheduler, map location) -- the automatic choice, both layouts with the
+            # TMA-staged shared-memory map (mbarrier + cp.async.bulk), block-synchronous rounds
+            knobs = [(0, -1, 2), (1024, 0, 1), (256, 0, 1), (256, 1, 0)] if k == 0 else [(0, -1, 2)]
+            for block, group, smem in knobs:
+                r.set_option(10, block); r.set_option(11, group); r.set_option(12, smem)
+                for count in (True, False):
+                    r.set_volume(vol)
+                    r.clear_accum(kw["width"], kw["height"])
+                    r.count_work(count)
+                    r.render_frame(opts, mcs)
+                    px = r.read_accum()
+                    argb = r.tonemap(opts[0])
+                    if ref is None:
+                        ref = px
+                    assert np.array_equal(px.view(np.uint32), ref.view(np.uint32)), (k, count, block, group, smem)
+                print(f"kernel {k} (block {block}, group {group}, smem {smem}): {kw['width']}x{kw['height']}x{kw['iters']} ok", flush=True)
+            r.set_option(10, 0); r.set_option(11, -1); r.set_option(12, 2)
     # the asynchronous read-back path and the accel rebuild kernels
     out = [r.alloc_pinned_argb() for _ in range(2)]
     r.set_option(2, 0)
