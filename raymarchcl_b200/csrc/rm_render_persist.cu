@@ -83,6 +83,9 @@ __device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
 #define RM_PERSIST_SMALL_T 256
 #define RM_PERSIST_SMALL_B 5
 #endif
+#ifndef RM_PERSIST_BIG_T
+#define RM_PERSIST_BIG_T 1024  // (measured, C2 ms: 1024 threads 30.78; 896 (72 registers) 32.05; 768 (80) 33.94; 640 (96) 36.63)
+#endif
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ PersistParams P) {
@@ -209,7 +212,7 @@ std::once_flag g_attr_once[64][64];
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 cudaError_t launch(const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev, cudaStream_t stream) {
   cudaError_t attr = cudaSuccess;
-  constexpr int variant = ((kThreads == 1024 ? 0 : 1) << 4) | (kCount ? 8 : 0) | kMap;
+  constexpr int variant = ((kThreads == RM_PERSIST_BIG_T && kBlocksPerSM == 1 ? 0 : 1) << 4) | (kCount ? 8 : 0) | kMap;
   std::call_once(g_attr_once[dev & 63][variant], [&] {
     if (kMap & fused::kMapNib) attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PERSIST_MAX_SMEM / kBlocksPerSM);
     else attr = cudaFuncSetAttribute(k_render_persist<kCount, kMap, kThreads, kBlocksPerSM>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -223,9 +226,9 @@ template <int kMap>
 cudaError_t launch_any(bool count, int threads, const RmShard& shard, const PersistParams& P, int blocks, size_t smem, int dev,
                        cudaStream_t stream) {
   // (the counting kernels visit every sample anyway: only the map's location matters to them)
-  if (count) return launch<true, kMap & fused::kMapNib, 1024, 1>(shard, P, blocks, smem, dev, stream);
+  if (count) return launch<true, kMap & fused::kMapNib, RM_PERSIST_BIG_T, 1>(shard, P, blocks, smem, dev, stream);
   if (threads == RM_PERSIST_SMALL_T) return launch<false, kMap, RM_PERSIST_SMALL_T, RM_PERSIST_SMALL_B>(shard, P, blocks, smem, dev, stream);
-  return launch<false, kMap, 1024, 1>(shard, P, blocks, smem, dev, stream);
+  return launch<false, kMap, RM_PERSIST_BIG_T, 1>(shard, P, blocks, smem, dev, stream);
 }
 
 }  // namespace
@@ -262,12 +265,13 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   const bool fits_big = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= (unsigned)RM_PERSIST_MAX_SMEM;
   const bool long_launch = P.bundles >= (long long)RM_PERSIST_AUTO_BUNDLES_PER_WARP * num_sms * 32;
   int threads;
-  if (d_counters) threads = 1024;
-  else if (block_threads == 0) threads = (smem_map != 0 && fits_big && long_launch) ? 1024 : RM_PERSIST_SMALL_T;
-  else threads = block_threads == 256 ? RM_PERSIST_SMALL_T : 1024;
-  const int blocks_per_sm = threads == 1024 ? 1 : RM_PERSIST_SMALL_B;
+  if (d_counters) threads = RM_PERSIST_BIG_T;
+  else if (block_threads == 0) threads = (smem_map != 0 && fits_big && long_launch) ? RM_PERSIST_BIG_T : RM_PERSIST_SMALL_T;
+  else threads = block_threads == 256 ? RM_PERSIST_SMALL_T : RM_PERSIST_BIG_T;
+  const bool big = threads == RM_PERSIST_BIG_T;
+  const int blocks_per_sm = big ? 1 : RM_PERSIST_SMALL_B;
   const bool fits = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
-  const bool use_nib = fits && (smem_map == 1 || (smem_map == 2 && threads == 1024));
+  const bool use_nib = fits && (smem_map == 1 || (smem_map == 2 && big));
   const int warps_per_block = threads / 32;
   long long blocks = (P.bundles + warps_per_block - 1) / warps_per_block;
   if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;
