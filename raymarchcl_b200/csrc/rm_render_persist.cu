@@ -86,10 +86,18 @@ __device__ __forceinline__ uint32_t tonemap_pack3(float3 p, float gamma) {
 #ifndef RM_PERSIST_BIG_T
 #define RM_PERSIST_BIG_T 1024  // (measured, C2 ms: 1024 threads 30.78; 896 (72 registers) 32.05; 768 (80) 33.94; 640 (96) 36.63)
 #endif
+#ifdef RM_PERSIST_TIMELINE
+__device__ unsigned long long g_tl_start[148 * 40], g_tl_first[148 * 40], g_tl_end[148 * 40];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 template <bool kCount, int kMap, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ PersistParams P) {
   const RmOpts& o = fused::g_opts;
+#ifdef RM_PERSIST_TIMELINE
+  const unsigned tl_id = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if ((threadIdx.x & 31) == 0 && tl_id < 148 * 40) g_tl_start[tl_id] = gtimer();
+#endif
   constexpr bool kNib = (kMap & fused::kMapNib) != 0;
   if (kNib) {
     // Stage the distance map: bulk async copies (TMA engine, no registers, no per-thread loads)
@@ -118,6 +126,9 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
   }
 
   const unsigned lane = threadIdx.x & 31u;
+#ifdef RM_PERSIST_TIMELINE
+  if (lane == 0 && tl_id < 148 * 40) g_tl_first[tl_id] = gtimer();
+#endif
   const int m = P.passes;
   const int sub = (int)lane / m, pass = (int)lane - sub * m;  // pixel of the bundle, pass of the launch
   const bool lane_used = sub < P.ppb;
@@ -191,6 +202,9 @@ k_render_persist(const __grid_constant__ RmShard sh, const __grid_constant__ Per
     }
   }
 
+#ifdef RM_PERSIST_TIMELINE
+  if (lane == 0 && tl_id < 148 * 40) g_tl_end[tl_id] = gtimer();
+#endif
   if constexpr (kCount) {
     unsigned long long a = cnt.steps, b = cnt.taps, c = cnt.outer;
     for (int off = 16; off > 0; off >>= 1) {
@@ -232,6 +246,16 @@ cudaError_t launch_any(bool count, int threads, const RmShard& shard, const Pers
 }
 
 }  // namespace
+
+#ifdef RM_PERSIST_TIMELINE
+extern "C" int rm_debug_timeline(unsigned long long* out /* 3 x 5920 */) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_tl_start, sizeof(g_tl_start));
+  cudaMemcpyFromSymbol(out + 148 * 40, g_tl_first, sizeof(g_tl_first));
+  cudaMemcpyFromSymbol(out + 2 * 148 * 40, g_tl_end, sizeof(g_tl_end));
+  return 0;
+}
+#endif
 
 cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, const RmAccel& accel,
                                      const float4* d_tables, const float* times, const float* blend, int passes,
