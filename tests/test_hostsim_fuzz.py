@@ -126,6 +126,18 @@ def test_random_options_on_the_gpu(checkers, gpu_renderer, seed, kernel):
         if count:
             assert [st["steps"], st["taps"], st["outer_iters"]] == [int(x) for x in ref_cnt]
     r.count_work(False)
+    if kernel == 0:  # the layout of long launches (1024 x 1, distance map staged into shared memory by TMA): same bits
+        try:
+            r.set_option(10, 1024)
+            r.set_option(12, 1)
+            r.set_volume(vol)
+            r.clear_accum(W, H)
+            r.render_frame(opts, mcs)
+            big = r.read_accum()
+        finally:
+            r.set_option(10, 0)
+            r.set_option(12, 2)
+        assert ((big.view(np.uint32) == out[False].view(np.uint32)) | (np.isnan(big) & np.isnan(out[False]))).all(), "layouts differ"
     r.set_option(2, 0)
     a, b = out[True].view(np.uint32), out[False].view(np.uint32)
     assert ((a == b) | (np.isnan(out[True]) & np.isnan(out[False]))).all(), "production and counting kernels differ"
