@@ -76,6 +76,28 @@ cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, i
 #define RM_PERSIST_DEFAULT_SMEM 2         // 0 never, 1 whenever the map fits the layout, 2 = with the 1024-thread layout only
 #define RM_PERSIST_DEFAULT_ROUND 0        // free-running warps (1 = block-synchronous rounds: faster while the code was 58 KB, slower at 47 KB)
 #define RM_PERSIST_AUTO_BUNDLES_PER_WARP 16  // "long launch": at least this many bundles per resident warp slot of the 1024 x 1 layout
+// Layout and map location of one launch of the default kernel (RM_OPT_PERSIST_BLOCK / _SMEM; block_threads 0 and
+// smem_map 2 = pick here). One 1024-thread block per SM with the 4-bit distance map staged into its shared memory by TMA
+// is the fastest form once a launch is long enough to pay for 148 blocks each pulling the map in (B200, C2: 30.99 ms
+// against 31.43 for 256 x 5 with the byte map in L1 / L2; C1's 2 048 bundles: 0.403 against 0.386); five 256-thread blocks
+// per SM each with a copy of the map are not (128^3: 30.18 against 30.03), so the automatic choice couples the two.
+// The counting kernels always run in the big layout. (Host-compiled by tests/hostsim: tests/test_host.py.)
+struct RmPersistLayout { int threads, blocks_per_sm, use_nib; };
+inline RmPersistLayout rm_persist_pick_layout(long long bundles, int num_sms, unsigned nib_bytes, int block_threads, int smem_map,
+                                              int counting, int small_threads = 256, int small_blocks = 5, int big_threads = 1024) {
+  const bool have_nib = nib_bytes > 0;
+  const bool fits_big = have_nib && nib_bytes <= (unsigned)RM_PERSIST_MAX_SMEM;
+  const bool long_launch = bundles >= (long long)RM_PERSIST_AUTO_BUNDLES_PER_WARP * num_sms * (big_threads / 32);
+  RmPersistLayout l;
+  if (counting) l.threads = big_threads;
+  else if (block_threads == 0) l.threads = (smem_map != 0 && fits_big && long_launch) ? big_threads : small_threads;
+  else l.threads = block_threads == 256 ? small_threads : big_threads;
+  const bool big = l.threads == big_threads;
+  l.blocks_per_sm = big ? 1 : small_blocks;
+  const bool fits = have_nib && nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / l.blocks_per_sm);
+  l.use_nib = (fits && (smem_map == 1 || (smem_map == 2 && big))) ? 1 : 0;
+  return l;
+}
 // How many of `available` consecutive fusable passes one launch should take: all (<= 32) when they
 // fill >= 80 % of a warp's lanes as whole pixels x passes groups, else the largest power of two.
 inline int rm_persist_pick_passes(int available) {

@@ -281,21 +281,10 @@ cudaError_t rm_launch_render_persist(const RmOpts& opts, const RmShard& shard, c
   P.bundles = (shard.slots + P.ppb - 1) / P.ppb;
   P.nib = accel.nib;
   P.nib_bytes = accel.nib_bytes;
-  // Layout and map location (RM_OPT_PERSIST_BLOCK / _SMEM; 0 / 2 = pick here). One 1024-thread block per SM with the
-  // 4-bit distance map staged into its shared memory by TMA is the fastest form once a launch is long enough to pay
-  // for 148 blocks each pulling the map in (B200, C2: 30.99 ms against 31.43 for 256 x 5 with the byte map in L1 / L2;
-  // C1's 2048 bundles: 0.403 against 0.386); five 256-thread blocks per SM with the map in shared memory are not
-  // (128^3: 30.18 against 30.03), so the automatic choice couples the two.
-  const bool fits_big = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= (unsigned)RM_PERSIST_MAX_SMEM;
-  const bool long_launch = P.bundles >= (long long)RM_PERSIST_AUTO_BUNDLES_PER_WARP * num_sms * 32;
-  int threads;
-  if (d_counters) threads = RM_PERSIST_BIG_T;
-  else if (block_threads == 0) threads = (smem_map != 0 && fits_big && long_launch) ? RM_PERSIST_BIG_T : RM_PERSIST_SMALL_T;
-  else threads = block_threads == 256 ? RM_PERSIST_SMALL_T : RM_PERSIST_BIG_T;
-  const bool big = threads == RM_PERSIST_BIG_T;
-  const int blocks_per_sm = big ? 1 : RM_PERSIST_SMALL_B;
-  const bool fits = accel.nib != nullptr && accel.nib_bytes > 0 && accel.nib_bytes <= (unsigned)(RM_PERSIST_MAX_SMEM / blocks_per_sm);
-  const bool use_nib = fits && (smem_map == 1 || (smem_map == 2 && big));
+  const RmPersistLayout lay = rm_persist_pick_layout(P.bundles, num_sms, accel.nib != nullptr ? accel.nib_bytes : 0u, block_threads, smem_map,
+                                                     d_counters != nullptr, RM_PERSIST_SMALL_T, RM_PERSIST_SMALL_B, RM_PERSIST_BIG_T);
+  const int threads = lay.threads, blocks_per_sm = lay.blocks_per_sm;
+  const bool use_nib = lay.use_nib != 0;
   const int warps_per_block = threads / 32;
   long long blocks = (P.bundles + warps_per_block - 1) / warps_per_block;
   if (blocks > (long long)num_sms * blocks_per_sm) blocks = (long long)num_sms * blocks_per_sm;

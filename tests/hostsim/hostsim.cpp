@@ -314,6 +314,11 @@ long long sim_shard_slots(int W, int H, int rank, int world, int tile_w, int til
 }
 
 int sim_pick_passes(int available) { return rm_persist_pick_passes(available); }
+// out[3] = threads, blocks per SM, map in shared memory
+void sim_pick_layout(long long bundles, int num_sms, unsigned nib_bytes, int block_threads, int smem_map, int counting, int* out) {
+  const RmPersistLayout l = rm_persist_pick_layout(bundles, num_sms, nib_bytes, block_threads, smem_map, counting);
+  out[0] = l.threads; out[1] = l.blocks_per_sm; out[2] = l.use_nib;
+}
 
 int sim_stats_words(void) { return (int)(sizeof(SimStats) / 8); }
 void sim_get_stats(unsigned long long* out, int reset) {

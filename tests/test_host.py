@@ -177,3 +177,35 @@ def test_packed_fp32_is_used_and_never_contracted():
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     assert len(re.findall(r"\bFADD2\b", sass)) > 100
     assert not re.findall(r"\b(FFMA2|FMUL2)\b", sass)
+
+
+def test_layout_choice_of_the_default_kernel():
+    """rm_persist_pick_layout (csrc/rm_kernels.h, compiled for the host by tests/hostsim): one 1024-thread block per SM with
+    the TMA-staged shared-memory distance map for long launches whose map fits, five 256-thread blocks with the byte map in
+    global memory otherwise; RM_OPT_PERSIST_BLOCK / _SMEM override either half."""
+    import ctypes as C
+    from tests.hostsim import build_hostsim
+    lib = C.CDLL(build_hostsim.build())
+    lib.sim_pick_layout.argtypes = [C.c_longlong, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+
+    def pick(bundles, nib_bytes, block=0, smem=2, counting=0, sms=148):
+        out = (C.c_int * 3)()
+        lib.sim_pick_layout(bundles, sms, nib_bytes, block, smem, counting, out)
+        return tuple(out)
+
+    c2 = 1920 * 1080 * 16 // 32
+    nib256 = 64 ** 3 // 2                                   # 128 KiB: C2's map
+    assert pick(c2, nib256) == (1024, 1, 1)                 # C2, one GPU
+    assert pick(c2 // 8, nib256) == (1024, 1, 1)            # one rank's shard of eight
+    assert pick(256 * 256 // 32, 16 ** 3 // 2) == (256, 5, 0)   # C1: a short launch does not pay for staging the map
+    assert pick(16 * 148 * 32 - 1, nib256) == (256, 5, 0) and pick(16 * 148 * 32, nib256) == (1024, 1, 1)  # the threshold
+    assert pick(c2, 160 * 160 * 33 // 2) == (256, 5, 0)     # 422 KB of nibbles: does not fit an SM
+    assert pick(c2, 0) == (256, 5, 0)                       # no 4-bit map built
+    assert pick(c2, nib256, smem=0) == (256, 5, 0)          # shared-memory map switched off
+    assert pick(c2, nib256, block=256) == (256, 5, 0)       # 5 x 128 KiB do not fit
+    assert pick(c2, 16 * 1024, block=256) == (256, 5, 0)    # ... and where they would, automatic mode still says no
+    assert pick(c2, 16 * 1024, block=256, smem=1) == (256, 5, 1)
+    assert pick(c2, nib256, block=1024, smem=0) == (1024, 1, 0)
+    assert pick(100, nib256, block=1024) == (1024, 1, 1)    # forced layout: the map comes along whenever it fits
+    assert pick(100, nib256, counting=1) == (1024, 1, 1)    # counting kernels: always the big layout
+    assert pick(100, nib256, counting=1, smem=0) == (1024, 1, 0)
