@@ -75,10 +75,12 @@ cudaError_t rm_launch_blend_passes(const float4* d_colour, const float* blend, i
 #define RM_PERSIST_DEFAULT_BLOCK 0        // 0 = chosen per launch (rm_launch_render_persist): 1024 x 1 + TMA-staged map for long launches, else 256 x 5
 #define RM_PERSIST_DEFAULT_SMEM 2         // 0 never, 1 whenever the map fits the layout, 2 = with the 1024-thread layout only
 #define RM_PERSIST_DEFAULT_ROUND 0        // free-running warps (1 = block-synchronous rounds: faster while the code was 58 KB, slower at 47 KB)
-#define RM_PERSIST_AUTO_BUNDLES_PER_WARP 16  // "long launch": at least this many bundles per resident warp slot of the 1024 x 1 layout
+#define RM_PERSIST_AUTO_BUNDLES_PER_WARP 4   // "long launch": at least this many bundles per resident warp slot of the 1024 x 1 layout
+                                            // (measured: 27 per slot, a 1/8 shard of C2: 4.08 vs 4.23 ms; 13.7, 960x540 x 4 passes: 2.45 vs
+                                            //  2.55; 0.43, C1: 0.403 vs 0.386 -- 2 048 bundles fill only 64 of the 148 big blocks)
 // Layout and map location of one launch of the default kernel (RM_OPT_PERSIST_BLOCK / _SMEM; block_threads 0 and
 // smem_map 2 = pick here). One 1024-thread block per SM with the 4-bit distance map staged into its shared memory by TMA
-// is the fastest form once a launch is long enough to pay for 148 blocks each pulling the map in (B200, C2: 30.99 ms
+// is the fastest form once a launch has enough bundles to fill 148 such blocks a few times over (B200, C2: 30.99 ms
 // against 31.43 for 256 x 5 with the byte map in L1 / L2; C1's 2 048 bundles: 0.403 against 0.386); five 256-thread blocks
 // per SM each with a copy of the map are not (128^3: 30.18 against 30.03), so the automatic choice couples the two.
 // The counting kernels always run in the big layout. (Host-compiled by tests/hostsim: tests/test_host.py.)
