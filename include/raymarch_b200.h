@@ -78,7 +78,7 @@ typedef enum rm_option {
                               4 = one thread per (pixel, pass) over the bit-brick volume + blend kernel
                               (round 1's default). All five produce identical results. */
   /* tuning knobs of the fast kernel; none of them changes results */
-  RM_OPT_CELL_SHIFT = 3,   /* macro-cell edge of the distance map = 1<<value voxels; 0 = auto (~res/64) */
+  RM_OPT_CELL_SHIFT = 3,   /* macro-cell edge of the distance map = 1<<value voxels; 0 = auto (4 voxels up to 1024^3) */
   RM_OPT_FUSE_LIMIT = 6,   /* max passes rendered by one launch (1..32) */
   RM_OPT_TRIP_LIMIT = 7,   /* watchdog of kernel 2: scheduling trips a warp may take per launch before
                               the launch is abandoned with RM_ERR_CUDA (default 2^28) */

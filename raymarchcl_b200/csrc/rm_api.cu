@@ -278,11 +278,17 @@ void guard_forget(rm_ctx* c) {
   if (g.owner == c) { g.owner = nullptr; g.done = nullptr; g.stream = nullptr; }
 }
 
+// Macro-cell edge of the distance map: one 4 x 4 x 4 brick (the cell index is then the brick index, the cheapest form of the
+// march loop, and skips are decided at the finest grain) as long as the byte map stays <= 32 MiB, i.e. up to 1024^3 voxels;
+// beyond that the smallest cell that fits. Round 1 kept the map at ~64^3 cells (8-voxel cells at 512^3, 16 at 1024^3) so that it
+// stayed L1-resident; with the leaner march loop of round 2 the finer map wins although it lives in L2 and cannot be staged
+// into shared memory: C3 (512^3) 29.67 vs 31.47 ms, C5 (1024^3) 38.46 vs 44.05 (profiles/r02_scheduling_ab.md 13).
 int auto_cell_shift(int rx, int ry, int rz) {
-  int m = rx > ry ? rx : ry;
-  m = m > rz ? m : rz;
-  int shift = 2;  // one brick
-  while ((m >> (shift + 1)) >= 64 && shift < 6) ++shift;  // cell ~ res/64 ~ 3 march steps
+  int shift = 2;
+  for (; shift < 6; ++shift) {
+    const long long mx = (rx + (1 << shift) - 1) >> shift, my = (ry + (1 << shift) - 1) >> shift, mz = (rz + (1 << shift) - 1) >> shift;
+    if (mx * my * mz <= (1LL << 25)) break;
+  }
   return shift;
 }
 
