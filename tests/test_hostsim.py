@@ -80,3 +80,18 @@ def test_ragged_grids(sim, orc, vres, mode):
     assert np.array_equal(px.view(np.uint32), ref.view(np.uint32))
     if mode in ("counting", "fused_counting"):
         assert np.array_equal(cnt, ref_cnt)
+
+
+def test_large_volume_with_brick_sized_cells(sim, orc):
+    """A 512^3 volume with the distance map at 4-voxel cells (128^3 cells: what rm_api.cu:auto_cell_shift picks up to
+    1024^3 since the end of round 2; 8-voxel cells until then): default kernel's routine over the byte map and over the
+    4-bit map, production and counting, bit for bit against the oracle."""
+    kw = dict(vres=512, width=64, height=36, iters=1, mat="metal", volume="blob")
+    vol, opts, mcs = build_scene(**kw)
+    ref, ref_cnt = orc.render_frame(vol, mcs, opts, kw["width"], kw["height"])
+    for mode, shift in (("fused_bytemap", 2), ("fused", 2), ("fused_counting", 2), ("fused_bytemap_counting", 2),
+                        ("production", 2), ("fused_bytemap", 3)):
+        px, cnt = sim.render_frame(vol, mcs, opts, kw["width"], kw["height"], mode=mode, cell_shift=shift)
+        assert np.array_equal(px.view(np.uint32), ref.view(np.uint32)), (mode, shift)
+        if mode.endswith("counting"):
+            assert np.array_equal(cnt, ref_cnt), (mode, shift)
